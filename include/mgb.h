@@ -1,0 +1,167 @@
+/*
+ * mgb.h — C ABI of libmgb200.so: the B200 (sm_100a) device path that sits under
+ * MyGrad's `Operation` protocol for conv_nd / max_pool and the gradient
+ * reductions of Tensor.backward.
+ *
+ * The reference (rsokl/MyGrad) has no FFI: its hot path is NumPy calls inside
+ * Python `Operation` subclasses.  Each entry point below names the reference
+ * code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, non-zero = error; the text is in
+ *     mgb_last_error() (thread-local).  Nothing throws.
+ *   - all pointers named x/w/y/dy/dx/dw/src/dst/ws are DEVICE pointers unless
+ *     the name starts with `host_`.  Tensors are C-contiguous.
+ *   - the library never allocates or retains caller buffers; scratch space is
+ *     passed in as (ws, ws_bytes) and sized by the *_workspace_bytes query.
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream).
+ *   - outputs are fully overwritten (no read-modify-write) except mgb_axpy and
+ *     mgb_reduce_broadcast(accumulate=1).
+ */
+#ifndef MGB_H_
+#define MGB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_MAX_SPATIAL 3
+#define MGB_MAX_DIMS 8
+
+typedef enum { MGB_F32 = 0, MGB_F64 = 1 } mgb_dtype;
+
+/* ---- convolution ------------------------------------------------------ */
+
+/* N-d cross-correlation descriptor: x (N,C,X...) * w (F,C,W...) -> y (N,F,G...)
+ * with G = (X + 2*pad - ((W-1)*dil + 1)) / stride + 1   (conv.py:63-74).
+ * nd = number of spatial dims (1..3); unused trailing entries are ignored. */
+typedef struct {
+  int32_t dtype;                 /* mgb_dtype */
+  int32_t nd;                    /* 1..MGB_MAX_SPATIAL */
+  int64_t N, C, F;
+  int64_t X[MGB_MAX_SPATIAL];
+  int64_t W[MGB_MAX_SPATIAL];
+  int64_t stride[MGB_MAX_SPATIAL];
+  int64_t pad[MGB_MAX_SPATIAL];
+  int64_t dil[MGB_MAX_SPATIAL];
+} mgb_conv_desc;
+
+/* which = 0 fwd, 1 dgrad (dX), 2 wgrad (dW) */
+int mgb_conv_workspace_bytes(const mgb_conv_desc* d, int which, size_t* bytes);
+
+/* y[n,f,g] = sum_{c,k} w[f,c,k] * xpad[n,c,g*s+k*d]
+ * replaces ConvND.__call__  (src/mygrad/nnet/layers/conv.py:15-103) */
+int mgb_conv_fwd(const mgb_conv_desc* d, const void* x, const void* w, void* y,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* dx[n,c,i] = sum_{f,k,g : g*s+k*d = i+p} dy[n,f,g] * w[f,c,k]
+ * replaces ConvND.backward_var(grad, 0)  (conv.py:105-138) */
+int mgb_conv_dgrad(const mgb_conv_desc* d, const void* dy, const void* w, void* dx,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* dw[f,c,k] = sum_{n,g} dy[n,f,g] * xpad[n,c,g*s+k*d]
+ * replaces ConvND.backward_var(grad, 1)  (conv.py:140-155) */
+int mgb_conv_wgrad(const mgb_conv_desc* d, const void* dy, const void* x, void* dw,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* ---- pooling ----------------------------------------------------------- */
+
+/* Pooling over the trailing `nd` axes of x (lead, X...) -> (lead, G...),
+ * G = (X - P)/stride + 1, no padding, no dilation (pooling.py:74-86). */
+typedef struct {
+  int32_t dtype;                 /* mgb_dtype */
+  int32_t nd;                    /* 1..MGB_MAX_SPATIAL */
+  int32_t mode;                  /* 0 = max, 1 = mean */
+  int32_t reserved;
+  int64_t lead;                  /* product of the un-pooled leading axes */
+  int64_t X[MGB_MAX_SPATIAL];
+  int64_t P[MGB_MAX_SPATIAL];
+  int64_t stride[MGB_MAX_SPATIAL];
+} mgb_pool_desc;
+
+/* replaces MaxPoolND.__call__  (src/mygrad/nnet/layers/pooling.py:13-98) */
+int mgb_pool_fwd(const mgb_pool_desc* d, const void* x, void* y, void* stream);
+
+/* dx[argmax-of-window(g)] += dy[g]; first max in row-major window order; NaN
+ * counts as max; overlapping windows accumulate in float64 in increasing flat
+ * window order, then cast to dtype.
+ * replaces MaxPoolND.backward_var  (pooling.py:100-149) */
+int mgb_pool_bwd(const mgb_pool_desc* d, const void* dy, const void* x, void* dx,
+                 void* stream);
+
+/* ---- Tensor.backward reductions / element-wise --------------------------- */
+
+/* out = (accumulate ? out : 0) + sum of g over the broadcast axes:
+ * leading extra axes of g are summed away, and axes where var_shape is 1 are
+ * summed with keepdims.  g_ndim >= v_ndim, both <= MGB_MAX_DIMS.
+ * replaces reduce_broadcast (src/mygrad/_utils/__init__.py:131-168) as called
+ * from Operation.grad_post_process_fn (src/mygrad/operation_base.py:89-105) */
+int mgb_reduce_broadcast(int dtype, int g_ndim, const int64_t* g_shape, int v_ndim,
+                         const int64_t* v_shape, const void* g, void* out,
+                         int accumulate, void* stream);
+
+/* dst[i] += src[i]   — `var._grad += backed_grad` (operation_base.py:227-228) */
+int mgb_axpy(int dtype, size_t n, const void* src, void* dst, void* stream);
+/* dst[i] = (dst_dtype) src[i] — np.copy / astype (operation_base.py:217-224) */
+int mgb_copy_cast(int src_dtype, int dst_dtype, size_t n, const void* src, void* dst,
+                  void* stream);
+/* dst[i] = value — np.full_like(data, 1.0) seed grad (tensor_base.py:1332) */
+int mgb_fill(int dtype, size_t n, double value, void* dst, void* stream);
+/* dst[i] *= alpha — used by the data-parallel wrapper (1/R for mean losses) */
+int mgb_scale(int dtype, size_t n, double alpha, void* dst, void* stream);
+
+/* ---- runtime plumbing -------------------------------------------------- */
+
+int mgb_device_count(int* count);
+int mgb_set_device(int ordinal);
+int mgb_get_device(int* ordinal);
+int mgb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+int mgb_malloc_async(void** ptr, size_t bytes, void* stream);
+int mgb_free_async(void* ptr, void* stream);
+int mgb_host_alloc(void** host_ptr, size_t bytes);      /* pinned */
+int mgb_host_free(void* host_ptr);
+int mgb_memcpy_h2d(void* dst, const void* host_src, size_t bytes, void* stream);
+int mgb_memcpy_d2h(void* host_dst, const void* src, size_t bytes, void* stream);
+int mgb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int mgb_memset(void* dst, int value, size_t bytes, void* stream);
+int mgb_stream_create(void** stream);
+int mgb_stream_destroy(void* stream);
+int mgb_stream_synchronize(void* stream);
+int mgb_device_synchronize(void);
+int mgb_event_create(void** event);
+int mgb_event_destroy(void* event);
+int mgb_event_record(void* event, void* stream);
+int mgb_event_synchronize(void* event);
+int mgb_event_elapsed_ms(void* start, void* stop, float* ms);
+int mgb_stream_wait_event(void* stream, void* event);
+/* number of kernels this library has launched in this process (bench.py's
+ * gpu_launches claim is read from here) */
+int mgb_launch_count(uint64_t* count);
+const char* mgb_last_error(void);
+const char* mgb_version(void);
+
+/* ---- multi-GPU (new; the reference has no communication layer) ------------ */
+
+/* NCCL communicator over the ranks of one node; id is ncclUniqueId bytes
+ * (128) produced by mgb_comm_unique_id on rank 0 and shipped by the caller. */
+int mgb_comm_unique_id(void* id128);
+int mgb_comm_init_rank(const void* id128, int world_size, int rank);
+int mgb_comm_destroy(void);
+/* in-place sum all-reduce of a gradient buffer (dW, bias grads) */
+int mgb_allreduce_sum(void* buf, size_t n, int dtype, void* stream);
+
+/* ---- measurement helpers (bench.py only) ---------------------------------- */
+
+/* Register-resident MMA loops that measure the tensor-pipe ceilings the
+ * roofline fractions are quoted against.  kind: 0 = FP64 DMMA m8n8k4,
+ * 1 = TF32 mma.sync m16n8k8.  Returns achieved TFLOP/s. */
+int mgb_probe_mma_peak(int kind, int iters, double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGB_H_ */

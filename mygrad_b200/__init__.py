@@ -1,0 +1,45 @@
+"""mygrad_b200 — B200-native (sm_100a) hot path for MyGrad's conv_nd / max_pool.
+
+The public surface mirrors the part of ``mygrad`` that the path touches:
+
+    from mygrad_b200 import Tensor, Operation, no_autodiff, execute_op
+    from mygrad_b200.nnet.layers import conv_nd, max_pool
+
+Arithmetic runs in hand-written CUDA kernels behind a C ABI (include/mgb.h), called
+through ctypes; tensors live in HBM as ``DeviceArray`` and are exchanged through
+``__cuda_array_interface__``.  There is no CPU fallback: importing this package
+without the built extension raises ImportError.
+"""
+from . import _graph_tracking
+from ._graph_tracking import no_autodiff
+from ._lib import LIB_PATH, lib
+from .device_array import (
+    DeviceArray,
+    asdevice,
+    current_stream,
+    device_available,
+    empty,
+    full,
+    full_like,
+    pinned_empty,
+    set_stream,
+    synchronize,
+    zeros,
+)
+from .errors import DisconnectedView, InvalidBackprop, InvalidGradient, SkipGradient
+from .operation_base import Operation
+from .tensor_base import Tensor, asarray, tensor
+from . import nnet
+from .nnet.layers import conv_nd, max_pool, mean_pool
+
+execute_op = Tensor._op  # same alias as mygrad.execute_op (src/mygrad/__init__.py:52)
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "Tensor", "tensor", "asarray", "Operation", "execute_op", "no_autodiff",
+    "DeviceArray", "asdevice", "empty", "zeros", "full", "full_like", "pinned_empty",
+    "current_stream", "set_stream", "synchronize", "device_available",
+    "InvalidGradient", "InvalidBackprop", "DisconnectedView", "SkipGradient",
+    "nnet", "conv_nd", "max_pool", "mean_pool", "lib", "LIB_PATH",
+]

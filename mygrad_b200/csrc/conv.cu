@@ -1,0 +1,464 @@
+// Host-side planning and C-ABI entry points for the implicit-GEMM convolutions.
+// Kernels are in conv_gemm.cuh; this file turns an mgb_conv_desc into gather
+// tables (built on the device, in the caller's workspace) and launches.
+#include <vector>
+
+#include "conv_gemm.cuh"
+
+namespace mgb {
+namespace conv {
+namespace {
+
+constexpr int kMaxW = 32;  // max filter extent per axis (dgrad residue tables are passed by value)
+
+struct Plan {
+  int dtype;
+  long long N, C, F;
+  int X[3], W[3], S[3], Pd[3], D[3], G[3];
+  long long Xp, Wp, Gp;  // products
+};
+
+int make_plan(const mgb_conv_desc* d, Plan* out) {
+  if (!d) return fail("conv: null descriptor");
+  if (d->dtype != MGB_F32 && d->dtype != MGB_F64) return fail("conv: bad dtype %d", d->dtype);
+  if (d->nd < 1 || d->nd > MGB_MAX_SPATIAL)
+    return fail("conv: %d spatial dims unsupported (1..%d)", d->nd, MGB_MAX_SPATIAL);
+  if (d->N < 0 || d->C < 0 || d->F < 0) return fail("conv: negative extent");
+  Plan p;
+  p.dtype = d->dtype;
+  p.N = d->N; p.C = d->C; p.F = d->F;
+  int shift = 3 - d->nd;
+  for (int i = 0; i < 3; ++i) { p.X[i] = 1; p.W[i] = 1; p.S[i] = 1; p.Pd[i] = 0; p.D[i] = 1; p.G[i] = 1; }
+  for (int i = 0; i < d->nd; ++i) {
+    long long X = d->X[i], W = d->W[i], S = d->stride[i], P = d->pad[i], D = d->dil[i];
+    if (X < 0 || W < 1 || S < 1 || P < 0 || D < 1)
+      return fail("conv: bad axis %d (X=%lld W=%lld stride=%lld pad=%lld dil=%lld)", i, X, W, S, P, D);
+    if (W > kMaxW) return fail("conv: filter extent %lld > %d unsupported", W, kMaxW);
+    long long num = X + 2 * P - ((W - 1) * D + 1);
+    if (num < 0 || num % S != 0)
+      return fail("conv: stride and kernel dimensions are incompatible on axis %d", i);
+    long long G = num / S + 1;
+    if (X + 2 * P > INT32_MAX / 4 || G > INT32_MAX / 4) return fail("conv: axis too long");
+    p.X[i + shift] = (int)X; p.W[i + shift] = (int)W; p.S[i + shift] = (int)S;
+    p.Pd[i + shift] = (int)P; p.D[i + shift] = (int)D; p.G[i + shift] = (int)G;
+  }
+  p.Xp = (long long)p.X[0] * p.X[1] * p.X[2];
+  p.Wp = (long long)p.W[0] * p.W[1] * p.W[2];
+  p.Gp = (long long)p.G[0] * p.G[1] * p.G[2];
+  const long long lim = INT32_MAX;
+  if (p.C * p.Xp > lim || p.F * p.Gp > lim) return fail("conv: per-sample extent exceeds int32");
+  if (p.N * p.Gp > lim || p.N * p.Xp > lim) return fail("conv: pixel count exceeds int32");
+  if (p.C * p.Wp > lim || p.F * p.Wp > lim) return fail("conv: filter bank too large");
+  *out = p;
+  return 0;
+}
+
+// ---- device-side table builders ------------------------------------------------
+
+struct XTableArgs {  // taps of the x-gather: index (c, t0, t1, t2)
+  int C, W[3], D[3], xs[3];
+  long long chan_stride;
+};
+
+__global__ void build_x_table(TapEntry* tab, XTableArgs a) {
+  int wp = a.W[0] * a.W[1] * a.W[2];
+  int total = a.C * wp;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+    int c = k / wp, t = k - c * wp;
+    int t2 = t % a.W[2]; t /= a.W[2];
+    int t1 = t % a.W[1];
+    int t0 = t / a.W[1];
+    TapEntry e;
+    e.d0 = t0 * a.D[0]; e.d1 = t1 * a.D[1]; e.d2 = t2 * a.D[2];
+    e.off = (int)(c * a.chan_stride + (long long)e.d0 * a.xs[0] + (long long)e.d1 * a.xs[1] +
+                  (long long)e.d2 * a.xs[2]);
+    tab[k] = e;
+  }
+}
+
+__global__ void build_chan_table(TapEntry* tab, int nchan, long long chan_stride) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nchan; k += gridDim.x * blockDim.x) {
+    TapEntry e;
+    e.off = (int)(k * chan_stride);
+    e.d0 = e.d1 = e.d2 = 0;
+    tab[k] = e;
+  }
+}
+
+// one stride-residue class of dgrad: the taps k with (r - k*dil) % stride == 0 per axis
+struct DgradClass {
+  int cnt[3];
+  short kidx[3][kMaxW];
+  short e[3][kMaxW];   // (r - k*dil)/stride, exact
+  int F, C, W[3], gs[3];
+  long long Gp;
+};
+
+// table over (f, tap_j) and packed weights wp[c][(f, tap_j)] = w[f][c][tap]
+template <typename T>
+__global__ void build_dgrad_class(TapEntry* tab, T* wpack, const T* __restrict__ w, DgradClass a) {
+  int ntap = a.cnt[0] * a.cnt[1] * a.cnt[2];
+  int K = a.F * ntap;
+  int wp = a.W[0] * a.W[1] * a.W[2];
+  long long total = (long long)K * (a.C + 1);  // slot C of each k builds the table entry
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i / K), k = (int)(i - (long long)c * K);
+    int f = k / ntap, j = k - f * ntap;
+    int j2 = j % a.cnt[2]; j /= a.cnt[2];
+    int j1 = j % a.cnt[1];
+    int j0 = j / a.cnt[1];
+    if (c == a.C) {
+      TapEntry e;
+      e.d0 = a.e[0][j0]; e.d1 = a.e[1][j1]; e.d2 = a.e[2][j2];
+      e.off = (int)(f * a.Gp + (long long)e.d0 * a.gs[0] + (long long)e.d1 * a.gs[1] +
+                    (long long)e.d2 * a.gs[2]);
+      tab[k] = e;
+    } else {
+      int tap = (a.kidx[0][j0] * a.W[1] + a.kidx[1][j1]) * a.W[2] + a.kidx[2][j2];
+      wpack[(long long)c * K + k] = w[((long long)f * a.C + c) * wp + tap];
+    }
+  }
+}
+
+template <typename T>
+__global__ void splitk_reduce(const T* __restrict__ partial, T* __restrict__ out, long long n,
+                              int splits) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int s = 0; s < splits; ++s) acc += (double)partial[(long long)s * n + i];  // fixed order
+    out[i] = (T)acc;
+  }
+}
+
+inline int small_grid(long long n) {
+  long long b = (n + 255) / 256;
+  long long cap = (long long)sm_count() * 8;
+  return (int)std::max(1LL, std::min(b, cap));
+}
+
+// ---- tile configurations ---------------------------------------------------------
+
+template <typename T> struct Tiles;
+template <> struct Tiles<double> {
+  using Big = Cfg<double, 128, 128, 16, 64, 32, 4>;    // 8 warps
+  using Mid = Cfg<double, 128, 64, 16, 32, 32, 4>;     // 8 warps
+  using Small = Cfg<double, 128, 32, 16, 32, 16, 4>;   // 8 warps
+  using WBig = Cfg<double, 128, 128, 16, 64, 32, 4>;
+  using WMid = Cfg<double, 64, 128, 16, 32, 32, 4>;
+  using WSmall = Cfg<double, 32, 128, 16, 16, 32, 4>;
+};
+template <> struct Tiles<float> {
+  using Big = Cfg<float, 128, 128, 32, 64, 32, 4>;
+  using Mid = Cfg<float, 128, 64, 32, 32, 32, 4>;
+  using Small = Cfg<float, 128, 32, 32, 32, 16, 4>;
+  using WBig = Cfg<float, 128, 128, 32, 64, 32, 4>;
+  using WMid = Cfg<float, 64, 128, 32, 32, 32, 4>;
+  using WSmall = Cfg<float, 32, 128, 32, 16, 32, 4>;
+};
+
+template <typename T, typename C>
+int launch_fwdlike(const FwdParams<T>& p, cudaStream_t st) {
+  static thread_local bool configured = false;
+  if (!configured) {
+    MGB_CUDA(cudaFuncSetAttribute(conv_fwdlike_kernel<T, C>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_FWD));
+    configured = true;
+  }
+  dim3 grid((p.M + C::BM - 1) / C::BM, (p.N + C::BN - 1) / C::BN);
+  conv_fwdlike_kernel<T, C><<<grid, C::THREADS, C::SMEM_FWD, st>>>(p);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int run_fwdlike(const FwdParams<T>& p, cudaStream_t st) {
+  if (p.M == 0 || p.N == 0) return 0;
+  if (p.N > 64) return launch_fwdlike<T, typename Tiles<T>::Big>(p, st);
+  if (p.N > 32) return launch_fwdlike<T, typename Tiles<T>::Mid>(p, st);
+  return launch_fwdlike<T, typename Tiles<T>::Small>(p, st);
+}
+
+template <typename C>
+void wgrad_shape(int M, int N, int K, int* tiles, int* splits, int* kps) {
+  int t = ((M + C::BM - 1) / C::BM) * ((N + C::BN - 1) / C::BN);
+  int kt = (K + C::BK - 1) / C::BK;
+  int sms = sm_count();
+  // fill the machine once or twice over; keep at least 8 k-slabs per split
+  int want = std::max(1, (2 * sms) / t);
+  int s = std::max(1, std::min(want, std::max(1, kt / 8)));
+  int per = (kt + s - 1) / s;   // slabs per split
+  s = (kt + per - 1) / per;
+  *tiles = t; *splits = std::max(1, s); *kps = per * C::BK;
+}
+
+// which wgrad tile family: by M (= F)
+inline int wgrad_family(int M) { return M > 64 ? 0 : (M > 32 ? 1 : 2); }
+
+template <typename T>
+void wgrad_plan(int M, int N, int K, int* splits, int* kps) {
+  int tiles;
+  switch (wgrad_family(M)) {
+    case 0: wgrad_shape<typename Tiles<T>::WBig>(M, N, K, &tiles, splits, kps); break;
+    case 1: wgrad_shape<typename Tiles<T>::WMid>(M, N, K, &tiles, splits, kps); break;
+    default: wgrad_shape<typename Tiles<T>::WSmall>(M, N, K, &tiles, splits, kps); break;
+  }
+}
+
+template <typename T, typename C>
+int launch_wgrad(const WgradParams<T>& p, int splits, cudaStream_t st) {
+  static thread_local bool configured = false;
+  if (!configured) {
+    MGB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<T, C>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_WGRAD));
+    configured = true;
+  }
+  dim3 grid((p.M + C::BM - 1) / C::BM, (p.N + C::BN - 1) / C::BN, splits);
+  conv_wgrad_kernel<T, C><<<grid, C::THREADS, C::SMEM_WGRAD, st>>>(p);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- geometry helpers ---------------------------------------------------------------
+
+GatherGeom geom_x_by_output(const Plan& p) {  // gather from x, pixels = output grid
+  GatherGeom g;
+  g.sample_stride = p.C * p.Xp;
+  for (int i = 0; i < 3; ++i) { g.P[i] = p.G[i]; g.pmul[i] = p.S[i]; g.base[i] = -p.Pd[i]; g.X[i] = p.X[i]; }
+  g.xs[2] = 1; g.xs[1] = p.X[2]; g.xs[0] = p.X[1] * p.X[2];
+  g.pp = (int)p.Gp;
+  return g;
+}
+
+GatherGeom geom_dy_by_output(const Plan& p) {  // gather from dy, pixels = output grid (1x1 taps)
+  GatherGeom g;
+  g.sample_stride = p.F * p.Gp;
+  for (int i = 0; i < 3; ++i) { g.P[i] = p.G[i]; g.pmul[i] = 1; g.base[i] = 0; g.X[i] = p.G[i]; }
+  g.xs[2] = 1; g.xs[1] = p.G[2]; g.xs[0] = p.G[1] * p.G[2];
+  g.pp = (int)p.Gp;
+  return g;
+}
+
+XTableArgs x_table_args(const Plan& p) {
+  XTableArgs a;
+  a.C = (int)p.C;
+  for (int i = 0; i < 3; ++i) { a.W[i] = p.W[i]; a.D[i] = p.D[i]; }
+  a.xs[2] = 1; a.xs[1] = p.X[2]; a.xs[0] = p.X[1] * p.X[2];
+  a.chan_stride = p.Xp;
+  return a;
+}
+
+inline long long ceil_div_ll(long long a, long long b) {  // b > 0
+  return a >= 0 ? (a + b - 1) / b : -((-a) / b);
+}
+
+struct DgradClassPlan {
+  DgradClass dev;
+  int Q[3], qlo[3], r[3];
+  int ntap;
+  long long K;        // F * ntap
+  size_t tab_off, wp_off;
+};
+
+// enumerate the stride-residue classes that own at least one dx element
+void dgrad_classes(const Plan& p, size_t esz, std::vector<DgradClassPlan>* out, size_t* ws_bytes) {
+  size_t off = 0;
+  for (int r0 = 0; r0 < p.S[0]; ++r0)
+    for (int r1 = 0; r1 < p.S[1]; ++r1)
+      for (int r2 = 0; r2 < p.S[2]; ++r2) {
+        int r[3] = {r0, r1, r2};
+        DgradClassPlan c;
+        bool empty = false;
+        c.ntap = 1;
+        for (int i = 0; i < 3; ++i) {
+          // padded coordinate s*q + r must land in [pad, X + pad)
+          long long qlo = ceil_div_ll(p.Pd[i] - r[i], p.S[i]);
+          long long qhi = ceil_div_ll((long long)p.X[i] + p.Pd[i] - r[i], p.S[i]);
+          c.qlo[i] = (int)qlo; c.Q[i] = (int)(qhi - qlo); c.r[i] = r[i];
+          if (c.Q[i] <= 0) empty = true;
+          int cnt = 0;
+          for (int k = 0; k < p.W[i]; ++k) {
+            int num = r[i] - k * p.D[i];
+            if (((num % p.S[i]) + p.S[i]) % p.S[i] == 0) {
+              c.dev.kidx[i][cnt] = (short)k;
+              c.dev.e[i][cnt] = (short)(num / p.S[i]);  // exact division
+              ++cnt;
+            }
+          }
+          c.dev.cnt[i] = cnt;
+          c.ntap *= cnt;
+        }
+        if (empty || c.ntap == 0) continue;  // nothing to write / stays zero from the memset
+        c.K = p.F * c.ntap;
+        c.dev.F = (int)p.F; c.dev.C = (int)p.C;
+        for (int i = 0; i < 3; ++i) c.dev.W[i] = p.W[i];
+        c.dev.gs[2] = 1; c.dev.gs[1] = p.G[2]; c.dev.gs[0] = p.G[1] * p.G[2];
+        c.dev.Gp = p.Gp;
+        c.tab_off = off; off += align_up((size_t)c.K * sizeof(TapEntry), 256);
+        c.wp_off = off;  off += align_up((size_t)c.K * p.C * esz, 256);
+        out->push_back(c);
+      }
+  *ws_bytes = off;
+}
+
+bool dgrad_needs_memset(const Plan& p, const std::vector<DgradClassPlan>& cls) {
+  long long covered = 0;
+  for (auto& c : cls) covered += (long long)c.Q[0] * c.Q[1] * c.Q[2];
+  return covered != p.Xp;
+}
+
+// ---- the three convolutions ------------------------------------------------------------
+
+template <typename T>
+int fwd_t(const Plan& p, const T* x, const T* w, T* y, void* ws, size_t ws_bytes, cudaStream_t st) {
+  long long K = p.C * p.Wp, M = p.N * p.Gp;
+  if (M * p.F == 0) return 0;
+  if (K == 0) { MGB_CUDA(cudaMemsetAsync(y, 0, (size_t)(M * p.F) * sizeof(T), st)); return 0; }
+  size_t need = (size_t)K * sizeof(TapEntry);
+  if (ws_bytes < need || !ws) return fail("conv fwd: workspace %zu < %zu bytes", ws_bytes, need);
+  TapEntry* tab = (TapEntry*)ws;
+  build_x_table<<<small_grid(K), 256, 0, st>>>(tab, x_table_args(p));
+  MGB_LAUNCH_CHECK();
+  FwdParams<T> fp;
+  fp.src = x; fp.tab = tab; fp.B = w; fp.ldb = K; fp.out = y;
+  fp.ga = geom_x_by_output(p);
+  fp.om.sample_stride = p.F * p.Gp; fp.om.chan_stride = p.Gp;
+  for (int i = 0; i < 3; ++i) { fp.om.omul[i] = 1; fp.om.obase[i] = 0; }
+  fp.om.os[2] = 1; fp.om.os[1] = p.G[2]; fp.om.os[0] = p.G[1] * p.G[2];
+  fp.M = (int)M; fp.N = (int)p.F; fp.K = (int)K;
+  return run_fwdlike<T>(fp, st);
+}
+
+template <typename T>
+int dgrad_t(const Plan& p, const T* dy, const T* w, T* dx, void* ws, size_t ws_bytes,
+            cudaStream_t st) {
+  long long n_dx = p.N * p.C * p.Xp;
+  if (n_dx == 0) return 0;
+  if (p.F * p.Gp * p.Wp == 0) { MGB_CUDA(cudaMemsetAsync(dx, 0, (size_t)n_dx * sizeof(T), st)); return 0; }
+  std::vector<DgradClassPlan> cls;
+  size_t need = 0;
+  dgrad_classes(p, sizeof(T), &cls, &need);
+  if (ws_bytes < need || (need && !ws)) return fail("conv dgrad: workspace %zu < %zu bytes", ws_bytes, need);
+  if (dgrad_needs_memset(p, cls)) MGB_CUDA(cudaMemsetAsync(dx, 0, (size_t)n_dx * sizeof(T), st));
+  for (auto& c : cls) {
+    TapEntry* tab = (TapEntry*)((char*)ws + c.tab_off);
+    T* wpack = (T*)((char*)ws + c.wp_off);
+    build_dgrad_class<T><<<small_grid(c.K * (p.C + 1)), 256, 0, st>>>(tab, wpack, w, c.dev);
+    MGB_LAUNCH_CHECK();
+    FwdParams<T> fp;
+    fp.src = dy; fp.tab = tab; fp.B = wpack; fp.ldb = c.K; fp.out = dx;
+    fp.ga.sample_stride = p.F * p.Gp;
+    for (int i = 0; i < 3; ++i) {
+      fp.ga.P[i] = c.Q[i]; fp.ga.pmul[i] = 1; fp.ga.base[i] = c.qlo[i]; fp.ga.X[i] = p.G[i];
+      fp.om.omul[i] = p.S[i];
+      fp.om.obase[i] = p.S[i] * c.qlo[i] + c.r[i] - p.Pd[i];
+    }
+    fp.ga.xs[2] = 1; fp.ga.xs[1] = p.G[2]; fp.ga.xs[0] = p.G[1] * p.G[2];
+    fp.ga.pp = c.Q[0] * c.Q[1] * c.Q[2];
+    fp.om.sample_stride = p.C * p.Xp; fp.om.chan_stride = p.Xp;
+    fp.om.os[2] = 1; fp.om.os[1] = p.X[2]; fp.om.os[0] = p.X[1] * p.X[2];
+    fp.M = (int)(p.N * fp.ga.pp); fp.N = (int)p.C; fp.K = (int)c.K;
+    if (run_fwdlike<T>(fp, st)) return 1;
+  }
+  return 0;
+}
+
+template <typename T>
+size_t wgrad_ws(const Plan& p, int* splits, int* kps) {
+  int M = (int)p.F, N = (int)(p.C * p.Wp), K = (int)(p.N * p.Gp);
+  wgrad_plan<T>(M, N, K, splits, kps);
+  size_t off = align_up((size_t)M * sizeof(TapEntry), 256);
+  off += align_up((size_t)N * sizeof(TapEntry), 256);
+  off += (size_t)(*splits) * M * N * sizeof(T);
+  return off;
+}
+
+template <typename T>
+int wgrad_t(const Plan& p, const T* dy, const T* x, T* dw, void* ws, size_t ws_bytes,
+            cudaStream_t st) {
+  int M = (int)p.F, N = (int)(p.C * p.Wp), K = (int)(p.N * p.Gp);
+  if ((long long)M * N == 0) return 0;
+  if (K == 0) { MGB_CUDA(cudaMemsetAsync(dw, 0, (size_t)M * N * sizeof(T), st)); return 0; }
+  int splits, kps;
+  size_t need = wgrad_ws<T>(p, &splits, &kps);
+  if (ws_bytes < need || !ws) return fail("conv wgrad: workspace %zu < %zu bytes", ws_bytes, need);
+  TapEntry* tabA = (TapEntry*)ws;
+  TapEntry* tabB = (TapEntry*)((char*)ws + align_up((size_t)M * sizeof(TapEntry), 256));
+  T* partial = (T*)((char*)tabB + align_up((size_t)N * sizeof(TapEntry), 256));
+  build_chan_table<<<small_grid(M), 256, 0, st>>>(tabA, M, p.Gp);
+  MGB_LAUNCH_CHECK();
+  build_x_table<<<small_grid(N), 256, 0, st>>>(tabB, x_table_args(p));
+  MGB_LAUNCH_CHECK();
+  WgradParams<T> wp;
+  wp.srcA = dy; wp.tabA = tabA; wp.srcB = x; wp.tabB = tabB; wp.partial = partial;
+  wp.ga = geom_dy_by_output(p);
+  wp.gb = geom_x_by_output(p);
+  wp.M = M; wp.N = N; wp.K = K; wp.k_per_split = kps;
+  int rc;
+  switch (wgrad_family(M)) {
+    case 0: rc = launch_wgrad<T, typename Tiles<T>::WBig>(wp, splits, st); break;
+    case 1: rc = launch_wgrad<T, typename Tiles<T>::WMid>(wp, splits, st); break;
+    default: rc = launch_wgrad<T, typename Tiles<T>::WSmall>(wp, splits, st); break;
+  }
+  if (rc) return rc;
+  splitk_reduce<T><<<small_grid((long long)M * N), 256, 0, st>>>(partial, dw, (long long)M * N, splits);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+}  // namespace conv
+}  // namespace mgb
+
+using namespace mgb;
+using namespace mgb::conv;
+
+extern "C" int mgb_conv_workspace_bytes(const mgb_conv_desc* d, int which, size_t* bytes) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (!bytes) return fail("mgb_conv_workspace_bytes: null");
+  size_t esz = p.dtype == MGB_F32 ? 4 : 8;
+  size_t need = 0;
+  if (which == 0) {
+    need = (size_t)(p.C * p.Wp) * sizeof(TapEntry);
+  } else if (which == 1) {
+    std::vector<DgradClassPlan> cls;
+    dgrad_classes(p, esz, &cls, &need);
+  } else if (which == 2) {
+    int s, k;
+    if (p.F * p.C * p.Wp == 0 || p.N * p.Gp == 0) need = 0;
+    else need = p.dtype == MGB_F32 ? wgrad_ws<float>(p, &s, &k) : wgrad_ws<double>(p, &s, &k);
+  } else {
+    return fail("mgb_conv_workspace_bytes: which=%d", which);
+  }
+  *bytes = need;
+  return 0;
+}
+
+extern "C" int mgb_conv_fwd(const mgb_conv_desc* d, const void* x, const void* w, void* y,
+                            void* ws, size_t ws_bytes, void* stream) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (p.dtype == MGB_F32)
+    return fwd_t<float>(p, (const float*)x, (const float*)w, (float*)y, ws, ws_bytes, as_stream(stream));
+  return fwd_t<double>(p, (const double*)x, (const double*)w, (double*)y, ws, ws_bytes, as_stream(stream));
+}
+
+extern "C" int mgb_conv_dgrad(const mgb_conv_desc* d, const void* dy, const void* w, void* dx,
+                              void* ws, size_t ws_bytes, void* stream) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (p.dtype == MGB_F32)
+    return dgrad_t<float>(p, (const float*)dy, (const float*)w, (float*)dx, ws, ws_bytes, as_stream(stream));
+  return dgrad_t<double>(p, (const double*)dy, (const double*)w, (double*)dx, ws, ws_bytes, as_stream(stream));
+}
+
+extern "C" int mgb_conv_wgrad(const mgb_conv_desc* d, const void* dy, const void* x, void* dw,
+                              void* ws, size_t ws_bytes, void* stream) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (p.dtype == MGB_F32)
+    return wgrad_t<float>(p, (const float*)dy, (const float*)x, (float*)dw, ws, ws_bytes, as_stream(stream));
+  return wgrad_t<double>(p, (const double*)dy, (const double*)x, (double*)dw, ws, ws_bytes, as_stream(stream));
+}

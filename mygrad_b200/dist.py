@@ -1,0 +1,115 @@
+"""Batch-axis data parallelism: one process per GPU, dW / bias grads summed by NCCL.
+
+The reference has no notion of ranks.  Every output sample of conv
+fwd, dX, pool fwd and pool bwd depends only on the same input sample, so rank r of R
+works on ``x[lo:hi]`` with a full replica of the filters; only parameter gradients
+(dW, broadcast biases) contract over the batch and need one sum all-reduce.  The
+result to match is the single-process reference on the full batch.
+
+``torch.distributed`` is used for rendezvous only (shipping the NCCL unique id and
+barriers); the all-reduce itself is ``mgb_allreduce_sum`` (ncclAllReduce on a side
+stream, ordered against the compute stream with events, so it can overlap dX).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+from ._lib import check, lib
+from .device_array import DeviceArray, current_stream
+
+__all__ = ["shard_bounds", "scale_for_mean_loss", "DataParallel"]
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """contiguous batch slice [lo, hi) of rank `rank`; the first n % world ranks get one extra"""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def scale_for_mean_loss(local_n: int, global_n: int) -> float:
+    """factor for a loss that averages over the LOCAL batch (e.g. softmax_crossentropy,
+    nnet/losses/softmax_crossentropy.py:41,46) so that the summed all-reduce equals the
+    full-batch mean gradient"""
+    return float(local_n) / float(global_n)
+
+
+class DataParallel:
+    """Owns the per-process NCCL communicator and a communication stream."""
+
+    def __init__(self, rank: Optional[int] = None, world_size: Optional[int] = None,
+                 local_rank: Optional[int] = None):
+        self.rank = int(os.environ.get("RANK", 0)) if rank is None else rank
+        self.world_size = int(os.environ.get("WORLD_SIZE", 1)) if world_size is None else world_size
+        self.local_rank = int(os.environ.get("LOCAL_RANK", self.rank)) if local_rank is None else local_rank
+        self._comm_stream = None
+        self._event = None
+        self._ready = False
+
+    # -- setup ---------------------------------------------------------------------
+    def init(self) -> "DataParallel":
+        """binds this process to GPU `local_rank` and creates the communicator; with
+        world_size > 1 a torch.distributed process group must already be initialised"""
+        check(lib.mgb_set_device(self.local_rank))
+        s, e = C.c_void_p(), C.c_void_p()
+        check(lib.mgb_stream_create(C.byref(s)))
+        check(lib.mgb_event_create(C.byref(e)))
+        self._comm_stream, self._event = s, e
+        if self.world_size > 1:
+            import torch.distributed as dist
+
+            if not dist.is_initialized():
+                raise RuntimeError("torch.distributed must be initialised before DataParallel.init()")
+            uid = (C.c_char * 128)()
+            if self.rank == 0:
+                check(lib.mgb_comm_unique_id(uid))
+            box = [bytes(uid.raw) if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            buf = (C.c_char * 128).from_buffer_copy(box[0])
+            check(lib.mgb_comm_init_rank(buf, self.world_size, self.rank))
+        self._ready = True
+        return self
+
+    def close(self) -> None:
+        if self._ready and self.world_size > 1:
+            lib.mgb_comm_destroy()
+        if self._comm_stream is not None:
+            lib.mgb_stream_destroy(self._comm_stream)
+            lib.mgb_event_destroy(self._event)
+            self._comm_stream = self._event = None
+        self._ready = False
+
+    # -- sharding --------------------------------------------------------------------
+    def shard(self, n: int) -> Tuple[int, int]:
+        return shard_bounds(n, self.rank, self.world_size)
+
+    # -- gradient exchange -------------------------------------------------------------
+    def allreduce_async(self, grads: Iterable[DeviceArray]) -> None:
+        """sum all-reduce of each buffer on the communication stream, after everything
+        already queued on the compute stream (later compute work overlaps with it)"""
+        if self.world_size == 1:
+            return
+        grads = list(grads)
+        compute = C.c_void_p(current_stream())
+        check(lib.mgb_event_record(self._event, compute))
+        check(lib.mgb_stream_wait_event(self._comm_stream, self._event))
+        for g in grads:
+            check(lib.mgb_allreduce_sum(C.c_void_p(g.ptr), C.c_size_t(g.size), g.code, self._comm_stream))
+
+    def wait(self) -> None:
+        """makes the compute stream wait for the outstanding all-reduces"""
+        if self.world_size == 1:
+            return
+        check(lib.mgb_event_record(self._event, self._comm_stream))
+        check(lib.mgb_stream_wait_event(C.c_void_p(current_stream()), self._event))
+
+    def allreduce(self, grads: Sequence[DeviceArray], scale: Optional[float] = None) -> None:
+        self.allreduce_async(grads)
+        self.wait()
+        if scale is not None and scale != 1.0:
+            for g in grads:
+                g *= scale

@@ -1,0 +1,5 @@
+"""``mygrad.nnet.layers`` entry points served by the B200 path (layers/__init__.py:1-5)."""
+from .conv import ConvND, conv_nd
+from .pooling import MaxPoolND, MeanPoolND, max_pool, mean_pool
+
+__all__ = ["conv_nd", "max_pool", "mean_pool", "ConvND", "MaxPoolND", "MeanPoolND"]

@@ -1,0 +1,164 @@
+"""conv_nd on B200: N-d cross-correlation forward, dX and dW as implicit-GEMM kernels.
+
+Drop-in for ``mygrad.nnet.layers.conv_nd`` / ``ConvND``
+(src/mygrad/nnet/layers/conv.py:14-155 op, :158-395 wrapper): same signature, same
+attributes set on the op (``variables, padding, stride, dilation``), same exception
+types (AssertionError for malformed stride/padding/dilation, ValueError for
+incompatible shapes), same output layout ``(N, F, G0, ...)``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from numbers import Integral
+from typing import Optional, Tuple, Union
+
+import numpy as np
+
+from ..._lib import ConvDesc, check, lib
+from ...device_array import DeviceArray, current_stream
+from ...operation_base import Operation
+from ...tensor_base import Tensor
+
+__all__ = ["conv_nd", "ConvND"]
+
+_MAX_SPATIAL = 3
+
+
+def _as_tuple(value, n: int, *, minimum: int, name: str) -> Tuple[int, ...]:
+    """int -> n-tuple; sequences must have length n and integer entries >= minimum.
+    Violations are AssertionErrors, as in the reference (conv.py:35-61)."""
+    if isinstance(value, Integral):
+        out = (int(value),) * n
+        ok = value >= minimum
+    else:
+        seq = list(value)
+        ok = len(seq) == n and all(isinstance(v, Integral) and v >= minimum for v in seq)
+        out = tuple(int(v) for v in seq) if ok else ()
+    assert ok, f"`{name}` must be an integer or a length-{n} sequence of integers >= {minimum}"
+    return out
+
+
+class ConvND(Operation):
+    def __call__(self, x: Tensor, w: Tensor, *, stride, padding=0, dilation=1) -> DeviceArray:
+        self.variables = (x, w)
+        xd, wd = x.data, w.data  # (N, C, X0, ...), (F, C, W0, ...)
+
+        assert xd.ndim > 2
+        assert xd.ndim == wd.ndim
+        assert wd.shape[1] == xd.shape[1], "The channel-depth of the batch and filters must agree"
+
+        nd = wd.ndim - 2
+        x_shape, w_shape = xd.shape[2:], wd.shape[2:]
+        dilation = _as_tuple(dilation, nd, minimum=1, name="dilation")
+        padding = _as_tuple(padding, nd, minimum=0, name="padding")
+        stride = _as_tuple(stride, nd, minimum=1, name="stride")
+
+        out_shape = []
+        ok = True
+        for X, W, s, p, d in zip(x_shape, w_shape, stride, padding, dilation):
+            num = X + 2 * p - ((W - 1) * d + 1)
+            ok = ok and num >= 0 and num % s == 0
+            out_shape.append(num // s + 1)
+        if not ok:
+            raise ValueError(
+                "Stride and kernel dimensions are incompatible: \n"
+                f"Input dimensions: {tuple(x_shape)}\n"
+                f"Stride dimensions: {tuple(stride)}\n"
+                f"Kernel dimensions: {tuple(w_shape)}\n"
+                f"Padding dimensions: {tuple(padding)}\n"
+                f"Dilation dimensions: {tuple(dilation)}\n"
+            )
+        if nd > _MAX_SPATIAL:
+            raise NotImplementedError(
+                f"the B200 path convolves over at most {_MAX_SPATIAL} spatial dims, got {nd}"
+            )
+
+        self.padding = np.array(padding, dtype=int)
+        self.stride = np.array(stride, dtype=int)
+        self.dilation = np.array(dilation, dtype=int)
+
+        # NumPy promotion of (x, w): f32*f32 -> f32, anything with f64 -> f64
+        self._dtype = np.result_type(xd.dtype, wd.dtype)
+        self._desc = ConvDesc()
+        d = self._desc
+        d.dtype = 0 if self._dtype == np.float32 else 1
+        d.nd = nd
+        d.N, d.C, d.F = xd.shape[0], xd.shape[1], wd.shape[0]
+        for i in range(nd):
+            d.X[i], d.W[i] = x_shape[i], w_shape[i]
+            d.stride[i], d.pad[i], d.dil[i] = stride[i], padding[i], dilation[i]
+
+        xin, win = self._operands()
+        y = DeviceArray((xd.shape[0], wd.shape[0], *out_shape), self._dtype)
+        ws, ws_bytes = self._workspace(0)
+        check(lib.mgb_conv_fwd(C.byref(d), C.c_void_p(xin.ptr), C.c_void_p(win.ptr),
+                               C.c_void_p(y.ptr), C.c_void_p(ws.ptr if ws else 0),
+                               C.c_size_t(ws_bytes), C.c_void_p(current_stream())))
+        return y
+
+    # operands in the compute dtype (mixed f32/f64 inputs are promoted, as NumPy does)
+    def _operands(self) -> Tuple[DeviceArray, DeviceArray]:
+        x, w = (v.data for v in self.variables)
+        return x.astype(self._dtype, copy=False), w.astype(self._dtype, copy=False)
+
+    def _workspace(self, which: int):
+        n = C.c_size_t(0)
+        check(lib.mgb_conv_workspace_bytes(C.byref(self._desc), which, C.byref(n)))
+        if n.value == 0:
+            return None, 0
+        return DeviceArray((n.value + 7) // 8, np.float64), n.value
+
+    def backward_var(self, grad: DeviceArray, index: int, **kwargs) -> DeviceArray:
+        x, w = (v.data for v in self.variables)
+        xin, win = self._operands()
+        g = grad.astype(self._dtype, copy=False)
+        stream = C.c_void_p(current_stream())
+        if index == 0:  # dX, shape of x, dtype of x (conv.py:118)
+            dx = DeviceArray(x.shape, self._dtype)
+            ws, ws_bytes = self._workspace(1)
+            check(lib.mgb_conv_dgrad(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(win.ptr),
+                                     C.c_void_p(dx.ptr), C.c_void_p(ws.ptr if ws else 0),
+                                     C.c_size_t(ws_bytes), stream))
+            return dx.astype(x.dtype, copy=False)
+        else:  # dW, shape of w
+            dw = DeviceArray(w.shape, self._dtype)
+            ws, ws_bytes = self._workspace(2)
+            check(lib.mgb_conv_wgrad(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(xin.ptr),
+                                     C.c_void_p(dw.ptr), C.c_void_p(ws.ptr if ws else 0),
+                                     C.c_size_t(ws_bytes), stream))
+            return dw
+
+
+def conv_nd(
+    x,
+    filter_bank,
+    *,
+    stride: Union[int, Tuple[int, ...]],
+    padding: Union[int, Tuple[int, ...]] = 0,
+    dilation: Union[int, Tuple[int, ...]] = 1,
+    constant: Optional[bool] = None,
+) -> Tensor:
+    """N-dimensional cross-correlation of the batch `x` (N, C, X0, ...) with the filter
+    bank (F, C, W0, ...) -> (N, F, G0, ...), G = (X + 2p - ((W-1)d + 1))/s + 1.
+
+    Signature, validation and graph behaviour follow ``mygrad.nnet.layers.conv_nd``
+    (conv.py:158-166, 373-395); the arithmetic runs on the GPU.
+    """
+    if x.ndim < 3:
+        raise ValueError(f"`x` must possess at least three dimensions, got {x.ndim} dimensions")
+    if x.ndim != filter_bank.ndim:
+        raise ValueError(
+            f"`x` ({x.ndim}-dimensions) must have the same dimensionality as "
+            f"`filter_bank` ({filter_bank.ndim}-dimensions)"
+        )
+    if filter_bank.shape[1] != x.shape[1]:
+        raise ValueError(
+            f"`x.shape[1]` ({x.shape[1]}) must match `filter_bank.shape[1]` ({filter_bank.shape[1]})"
+        )
+    return Tensor._op(
+        ConvND,
+        x,
+        filter_bank,
+        op_kwargs={"stride": stride, "padding": padding, "dilation": dilation},
+        constant=constant,
+    )

@@ -1,0 +1,220 @@
+"""Generates the golden vectors in tests/golden/*.npz by running the LIVE reference
+(rsokl/MyGrad, imported from /root/reference/src or baseline/_ref) on seeded inputs.
+
+Run in the build container only (the GPU box has no reference checkout):
+
+    python tests/golden/make_golden.py
+
+Every case stores its inputs, its parameters (JSON) and the reference's outputs
+(forward value, x.grad, w.grad as left by Tensor.backward).  The fixtures pin the
+behaviours the reference's own tests do not: pool tie-breaking, NaN/inf routing,
+overlapping-window accumulation, fp32 / mixed-dtype convolution, strided+dilated dX,
+zero-size inputs, and grad accumulation / un-broadcast semantics of Operation.backward.
+"""
+from __future__ import annotations
+
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+for cand in (Path("/root/reference/src"), HERE.parent.parent / "baseline" / "_ref"):
+    if (cand / "mygrad").exists():
+        sys.path.insert(0, str(cand))
+        break
+import mygrad as mg  # noqa: E402
+from mygrad.nnet.layers import conv_nd, max_pool  # noqa: E402
+from mygrad.nnet.layers.utils import sliding_window_view  # noqa: E402
+
+
+def rng_arr(seed, shape, dtype):
+    return np.random.default_rng(seed).standard_normal(shape).astype(dtype)
+
+
+# ---- convolution: value + both gradients for a random upstream grad ------------------
+CONV_CASES = [
+    # name, x_shape, w_shape, stride, padding, dilation, x_dtype, w_dtype
+    ("c1d_basic", (2, 3, 9), (4, 3, 3), 1, 0, 1, "f8", "f8"),
+    ("c1d_s2_p1", (3, 2, 10), (5, 2, 4), 2, 1, 1, "f8", "f8"),
+    ("c1d_d2", (2, 2, 11), (3, 2, 3), 1, 2, 2, "f8", "f8"),
+    ("c2d_mixed_stride", (2, 3, 7, 8), (4, 3, 3, 2), (1, 2), (1, 0), 1, "f8", "f8"),
+    ("c2d_s2_p1", (3, 2, 9, 9), (5, 2, 3, 3), 2, 1, 1, "f8", "f8"),
+    ("c2d_s2_d2", (2, 2, 13, 13), (3, 2, 3, 3), 2, 0, 2, "f8", "f8"),
+    ("c2d_s3_d2_p2", (2, 3, 11, 11), (4, 3, 2, 3), (3, 2), (2, 1), (2, 1), "f8", "f8"),
+    ("c2d_1x1", (2, 5, 6, 6), (7, 5, 1, 1), 1, 0, 1, "f8", "f8"),
+    ("c2d_f32", (3, 4, 10, 10), (6, 4, 3, 3), 1, 1, 1, "f4", "f4"),
+    ("c2d_f32_s2", (2, 8, 12, 12), (16, 8, 4, 4), 2, 1, 1, "f4", "f4"),
+    ("c2d_x32_w64", (2, 3, 8, 8), (4, 3, 3, 3), 1, 1, 1, "f4", "f8"),
+    ("c2d_x64_w32", (2, 3, 8, 8), (4, 3, 3, 3), 1, 1, 1, "f8", "f4"),
+    ("c3d_basic", (2, 2, 5, 6, 7), (3, 2, 2, 3, 2), 1, (0, 1, 0), 1, "f8", "f8"),
+    ("c3d_s2_f32", (2, 3, 8, 8, 8), (4, 3, 2, 2, 2), 2, 0, 1, "f4", "f4"),
+    ("c3d_d2", (1, 2, 9, 7, 8), (2, 2, 2, 2, 3), 1, 1, (2, 1, 2), "f8", "f8"),
+    ("c2d_wide_channels", (2, 40, 6, 6), (70, 40, 3, 3), 1, 1, 1, "f8", "f8"),
+    ("c2d_tall_batch", (9, 2, 17, 19), (3, 2, 5, 3), 1, (2, 1), 1, "f8", "f8"),
+    ("config1_small_batch", (4, 3, 32, 32), (16, 3, 3, 3), 1, 1, 1, "f8", "f8"),
+]
+
+
+def run_conv_cases():
+    out, manifest = {}, {}
+    for i, (name, xs, ws, s, p, d, xdt, wdt) in enumerate(CONV_CASES):
+        x = rng_arr(100 + i, xs, xdt)
+        w = rng_arr(200 + i, ws, wdt)
+        xt, wt = mg.Tensor(x), mg.Tensor(w)
+        y = conv_nd(xt, wt, stride=s, padding=p, dilation=d)
+        g = rng_arr(300 + i, y.shape, y.dtype)
+        y.backward(g)
+        out[f"{name}/x"], out[f"{name}/w"], out[f"{name}/g"] = x, w, g
+        out[f"{name}/y"], out[f"{name}/dx"], out[f"{name}/dw"] = y.data, xt.grad, wt.grad
+        manifest[name] = {"stride": s, "padding": p, "dilation": d}
+    # zero-size spatial input that only exists through padding (test_conv.py:247-273)
+    for name, nd, pad in (("zero_size_1d", 1, 2), ("zero_size_2d", 2, (1, 3))):
+        pads = (pad,) * nd if isinstance(pad, int) else pad
+        x = np.zeros((1, 1) + (0,) * nd)
+        w = rng_arr(7, (1, 1) + tuple(2 * q for q in pads), "f8")
+        xt, wt = mg.Tensor(x), mg.Tensor(w)
+        y = conv_nd(xt, wt, stride=1, padding=pad)
+        y.backward()
+        out[f"{name}/x"], out[f"{name}/w"], out[f"{name}/g"] = x, w, np.ones(y.shape)
+        out[f"{name}/y"], out[f"{name}/dx"], out[f"{name}/dw"] = y.data, xt.grad, wt.grad
+        manifest[name] = {"stride": 1, "padding": pad, "dilation": 1}
+    np.savez_compressed(HERE / "conv_cases.npz", manifest=json.dumps(manifest), **out)
+    return len(manifest)
+
+
+# ---- pooling: value + gradient, including ties / NaN / inf / overlaps ----------------
+def pool_inputs():
+    r = np.random.default_rng(7)
+    cases = []
+    # (name, x, pool, stride)
+    cases.append(("p1d_overlap", r.standard_normal((2, 3, 11)).astype("f4"), (3,), 2))
+    cases.append(("p2d_tiled", r.standard_normal((2, 3, 8, 6)).astype("f8"), (2, 2), 2))
+    cases.append(("p2d_rect_overlap", r.standard_normal((2, 2, 9, 10)).astype("f4"), (3, 4), (2, 3)))
+    cases.append(("p2d_gaps", r.standard_normal((2, 2, 11, 11)).astype("f8"), (2, 2), 3))
+    cases.append(("p3d_tiled", r.standard_normal((2, 2, 4, 6, 8)).astype("f4"), (2, 2, 2), 2))
+    cases.append(("p3d_mixed", r.standard_normal((3, 5, 7, 9)).astype("f8"), (2, 3, 3), (1, 2, 3)))
+    cases.append(("p_no_lead", r.standard_normal((6, 8)).astype("f8"), (2, 2), 2))
+    cases.append(("p_trailing_only", r.standard_normal((3, 4, 5, 12)).astype("f4"), (4,), 4))
+    # ties: small integer alphabet, overlapping and tiled windows
+    ties = r.integers(0, 3, size=(2, 2, 8, 8)).astype("f4")
+    cases.append(("p2d_ties_tiled", ties, (2, 2), 2))
+    cases.append(("p2d_ties_overlap", ties, (3, 3), 1))
+    cases.append(("p2d_all_equal", np.ones((1, 1, 4, 4), "f8"), (2, 2), 2))
+    # NaN / inf routing
+    special = r.standard_normal((2, 1, 6, 6)).astype("f8")
+    special[0, 0, 0, 1] = np.nan
+    special[0, 0, 1, 0] = np.nan
+    special[0, 0, 2, 3] = np.inf
+    special[0, 0, 4, 4] = -np.inf
+    special[1, 0, 3, 3] = np.nan
+    special[1, 0, 5, 0] = np.inf
+    special[1, 0, 5, 1] = np.inf
+    cases.append(("p2d_special_tiled", special, (2, 2), 2))
+    cases.append(("p2d_special_overlap", special, (2, 2), 1))
+    cases.append(("p2d_special_f32", special.astype("f4"), (3, 3), 3))
+    # C1-shaped pool input at reduced batch
+    cases.append(("config1_pool", r.standard_normal((4, 16, 32, 32)).astype("f8"), (2, 2), 2))
+    return cases
+
+
+def run_pool_cases():
+    out, manifest = {}, {}
+    for i, (name, x, pool, stride) in enumerate(pool_inputs()):
+        xt = mg.Tensor(x)
+        y = max_pool(xt, pool, stride)
+        g = np.random.default_rng(400 + i).standard_normal(y.shape).astype(x.dtype)
+        y.backward(g)
+        # mean-pool has no reference function: the composed definition
+        nd = len(pool)
+        st = (stride,) * nd if isinstance(stride, int) else stride
+        win = sliding_window_view(x, pool, st)                       # (G..., lead..., P...)
+        mean = win.mean(axis=tuple(range(-nd, 0)))
+        axes = tuple(range(mean.ndim))
+        lead_nd = x.ndim - nd
+        mean = np.ascontiguousarray(mean.transpose(axes[nd:] + axes[:nd])) if lead_nd else mean
+        out[f"{name}/x"], out[f"{name}/g"] = x, g
+        out[f"{name}/y"], out[f"{name}/dx"], out[f"{name}/mean"] = y.data, xt.grad, mean
+        manifest[name] = {"pool": pool, "stride": stride}
+    np.savez_compressed(HERE / "pool_cases.npz", manifest=json.dumps(manifest), **out)
+    return len(manifest)
+
+
+# ---- whole layer through the reference's Tensor graph ---------------------------------
+LAYER_CASES = [
+    # name, x_shape, w_shape, stride, padding, dilation, pool, pool_stride, dtype
+    ("layer_c1_like", (4, 3, 16, 16), (8, 3, 3, 3), 1, 1, 1, (2, 2), 2, "f8"),
+    ("layer_c2_like_f32", (2, 8, 12, 12), (16, 8, 3, 3), 1, 1, 1, (2, 2), 2, "f4"),
+    ("layer_c3_like", (2, 4, 13, 13), (6, 4, 3, 3), 2, 0, 2, None, None, "f8"),
+    ("layer_c4_like_f32", (2, 3, 6, 8, 8), (4, 3, 3, 3, 3), 1, 0, 1, (2, 2, 2), 2, "f4"),
+    ("layer_overlap_pool", (2, 3, 9, 9), (4, 3, 3, 3), 1, 0, 1, (3, 3), 2, "f8"),
+]
+
+
+def run_layer_cases():
+    out, manifest = {}, {}
+    for i, (name, xs, ws, s, p, d, pool, ps, dt) in enumerate(LAYER_CASES):
+        x, w = rng_arr(500 + i, xs, dt), rng_arr(600 + i, ws, dt)
+        xt, wt = mg.Tensor(x), mg.Tensor(w)
+        y = conv_nd(xt, wt, stride=s, padding=p, dilation=d)
+        o = max_pool(y, pool, ps) if pool else y
+        o.backward()  # all-ones seed, like bench.py's step
+        out[f"{name}/x"], out[f"{name}/w"] = x, w
+        out[f"{name}/out"], out[f"{name}/conv"], out[f"{name}/dconv"] = o.data, y.data, y.grad
+        out[f"{name}/dx"], out[f"{name}/dw"] = xt.grad, wt.grad
+        manifest[name] = {"stride": s, "padding": p, "dilation": d, "pool": pool, "pool_stride": ps}
+    np.savez_compressed(HERE / "layer_cases.npz", manifest=json.dumps(manifest), **out)
+    return len(manifest)
+
+
+# ---- Operation.backward semantics: accumulation, un-broadcast, dtype casting -------------
+def run_graph_cases():
+    out = {}
+    r = np.random.default_rng(11)
+    # (1) one tensor consumed by two convs and a pool: grads accumulate (+=)
+    x = r.standard_normal((2, 2, 8, 8))
+    w1, w2 = r.standard_normal((3, 2, 3, 3)), r.standard_normal((3, 2, 3, 3))
+    xt, w1t, w2t = mg.Tensor(x), mg.Tensor(w1), mg.Tensor(w2)
+    total = conv_nd(xt, w1t, stride=1, padding=1) + conv_nd(xt, w2t, stride=1, padding=1)
+    o = max_pool(total, (2, 2), 2)
+    o.backward()
+    out.update({"acc/x": x, "acc/w1": w1, "acc/w2": w2, "acc/out": o.data, "acc/dx": xt.grad,
+                "acc/dw1": w1t.grad, "acc/dw2": w2t.grad, "acc/dtotal": total.grad})
+    # (2) broadcast bias: un-broadcast reduction (N,F,H,W) -> (1,F,1,1) and -> (F,1,1)
+    b4, b3 = r.standard_normal((1, 3, 1, 1)), r.standard_normal((3, 1, 1))
+    xt, w1t, b4t, b3t = mg.Tensor(x), mg.Tensor(w1), mg.Tensor(b4), mg.Tensor(b3)
+    y = conv_nd(xt, w1t, stride=1, padding=1) + b4t + b3t
+    g = r.standard_normal(y.shape)
+    y.backward(g)
+    out.update({"bias/b4": b4, "bias/b3": b3, "bias/g": g, "bias/y": y.data,
+                "bias/db4": b4t.grad, "bias/db3": b3t.grad, "bias/dx": xt.grad})
+    # (3) reduce_broadcast shape algebra on bare arrays
+    from mygrad._utils import reduce_broadcast
+    shapes = [((4, 3, 5, 6), (3, 1, 6)), ((4, 3, 5, 6), (1, 1, 1, 1)), ((4, 3, 5, 6), ()),
+              ((7, 5), (5,)), ((7, 5), (7, 1)), ((2, 3, 4, 5, 6), (3, 1, 5, 1)), ((6, 1, 4), (6, 1, 4)),
+              ((3, 4, 5), (4, 5)), ((64, 33, 7, 9), (1, 33, 1, 1))]
+    for i, (gs, vs) in enumerate(shapes):
+        a = r.standard_normal(gs)
+        out[f"rb{i}/g"], out[f"rb{i}/out"] = a, np.asarray(reduce_broadcast(a, vs))
+        out[f"rb{i}/vshape"] = np.array(vs, dtype=np.int64)
+    out["rb_count"] = np.array(len(shapes))
+    # (4) fp32 pool grad: float64 scatter buffer cast back to float32 by Operation.backward
+    xf = r.standard_normal((2, 2, 7, 7)).astype("f4")
+    xt = mg.Tensor(xf)
+    o = max_pool(xt, (3, 3), 2)
+    gf = r.standard_normal(o.shape).astype("f4")
+    o.backward(gf)
+    out.update({"pool32/x": xf, "pool32/g": gf, "pool32/dx": xt.grad})
+    np.savez_compressed(HERE / "graph_cases.npz", **out)
+    return 4
+
+
+if __name__ == "__main__":
+    print("reference:", mg.__file__)
+    print("conv cases:", run_conv_cases())
+    print("pool cases:", run_pool_cases())
+    print("layer cases:", run_layer_cases())
+    print("graph cases:", run_graph_cases())
+    for f in sorted(HERE.glob("*.npz")):
+        print(f.name, f.stat().st_size, "bytes")
