@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py — conv_nd + max_pool forward+backward throughput on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload C2|C2f64|C1|C3|C4]
+
+One "step" = one pass of the hot path over one synthetic batch through the public API:
+``out = max_pool(conv_nd(x, w, ...), pool, 2); out.backward()`` (conv fwd, pool fwd, pool
+bwd, conv dX, conv dW; plus the dW all-reduce when N > 1).  Prints ONE JSON line.
+
+* ``value``  — whole-job samples/s with x and w already resident in HBM.
+* ``e2e``    — same metric with HOST buffers: pinned x, w copied H2D and out, x.grad, w.grad
+               copied D2H inside the timed region, every step.
+* ``roofline`` — the slowest kernel of the step, algorithmic FLOPs (or bytes) over its
+               CUDA-event duration, against the measured peak.
+* ``cpu_baseline`` — the reference's NumPy path on the host cores (bounded sample).
+
+``--impl reference`` times the unmodified reference (baseline/_ref, else the oracle port)
+on the host cores for the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "conv_nd+max_pool fwd+bwd samples/sec"
+
+WORKLOADS = {
+    # BASELINE.json configs (C3 as written is rejected by the reference; 65x65 is the nearest valid shape)
+    "C1": dict(x=(32, 3, 32, 32), w=(16, 3, 3, 3), stride=1, padding=1, dilation=1, pool=(2, 2), dtype="f64"),
+    "C2": dict(x=(256, 64, 56, 56), w=(128, 64, 3, 3), stride=1, padding=1, dilation=1, pool=(2, 2), dtype="f32"),
+    "C2f64": dict(x=(256, 64, 56, 56), w=(128, 64, 3, 3), stride=1, padding=1, dilation=1, pool=(2, 2), dtype="f64"),
+    "C3": dict(x=(128, 128, 65, 65), w=(256, 128, 5, 5), stride=2, padding=0, dilation=2, pool=None, dtype="f64"),
+    "C4": dict(x=(4, 32, 32, 64, 64), w=(64, 32, 3, 3, 3), stride=1, padding=0, dilation=1, pool=(2, 2, 2), dtype="f32"),
+}
+NP_DTYPE = {"f32": np.float32, "f64": np.float64}
+
+
+def workload_name(name: str, cfg: dict) -> str:
+    x, w = cfg["x"], cfg["w"]
+    pool = f"+max_pool{'x'.join(map(str, cfg['pool']))}" if cfg["pool"] else ""
+    return (f"{name}: conv_nd x={x} w={w} stride={cfg['stride']} pad={cfg['padding']} "
+            f"dil={cfg['dilation']}{pool} {cfg['dtype']}")
+
+
+def geometry(cfg: dict):
+    nd = len(cfg["x"]) - 2
+    tup = lambda v: (v,) * nd if isinstance(v, int) else tuple(v)
+    s, p, d = tup(cfg["stride"]), tup(cfg["padding"]), tup(cfg["dilation"])
+    G = tuple((X + 2 * pi - ((W - 1) * di + 1)) // si + 1
+              for X, W, si, pi, di in zip(cfg["x"][2:], cfg["w"][2:], s, p, d))
+    N, Cc, F = cfg["x"][0], cfg["x"][1], cfg["w"][0]
+    flops = 2.0 * N * F * np.prod(G) * Cc * np.prod(cfg["w"][2:])   # per GEMM
+    esz = 4 if cfg["dtype"] == "f32" else 8
+    y_elems = N * F * int(np.prod(G))
+    p_elems = y_elems // int(np.prod(cfg["pool"])) if cfg["pool"] else 0
+    return dict(G=G, flops=float(flops), esz=esz, y_bytes=y_elems * esz, p_bytes=p_elems * esz,
+                x_bytes=int(np.prod(cfg["x"])) * esz, w_bytes=int(np.prod(cfg["w"])) * esz)
+
+
+def make_inputs(cfg: dict):
+    dt = NP_DTYPE[cfg["dtype"]]
+    x = np.random.default_rng(0).standard_normal(cfg["x"]).astype(dt)
+    w = np.random.default_rng(1).standard_normal(cfg["w"]).astype(dt)
+    return x, w
+
+
+# ---- clocks ---------------------------------------------------------------------------
+
+class ClockSampler:
+    """samples nvidia-smi while the timed region runs (B200_PROFILING.md clocks line)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # under load = the upper half of the samples (idle gaps between launches pull the tail down)
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---- reference arm ------------------------------------------------------------------------
+
+def load_reference():
+    """the unmodified reference (pure Python) if it travelled with the repo, else the oracle port"""
+    ref = ROOT / "baseline" / "_ref"
+    if (ref / "mygrad").exists():
+        sys.path.insert(0, str(ref))
+        try:
+            import mygrad as ref_mg
+            from mygrad.nnet.layers import conv_nd as r_conv, max_pool as r_pool
+
+            def step(x, w, cfg):
+                xt, wt = ref_mg.Tensor(x), ref_mg.Tensor(w)
+                y = r_conv(xt, wt, stride=cfg["stride"], padding=cfg["padding"], dilation=cfg["dilation"])
+                o = r_pool(y, cfg["pool"], 2) if cfg["pool"] else y
+                o.backward()
+                return o.data, xt.grad, wt.grad
+
+            return "reference", step
+        except Exception:
+            pass
+    from oracle import conv_pool_oracle as oc
+
+    def step(x, w, cfg):
+        return oc.layer_step(x, w, stride=cfg["stride"], padding=cfg["padding"], dilation=cfg["dilation"],
+                             pool=cfg["pool"], pool_stride=2)
+
+    return "port", step
+
+
+def host_threads() -> int:
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        if n:
+            return int(max(n))
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_sample(cfg: dict, budget_s: float, steps: int = 1, warmup: int = 0):
+    """times the reference on a batch-slice of the workload sized to ~budget_s in total"""
+    kind, step = load_reference()
+    x, w = make_inputs(dict(cfg, x=(min(2, cfg["x"][0]), *cfg["x"][1:])))
+    t0 = time.perf_counter()
+    step(x, w, cfg)
+    t_probe = (time.perf_counter() - t0) / x.shape[0]        # s per sample, cold
+    runs = max(1, steps + warmup)
+    b = int(max(1, min(cfg["x"][0], budget_s / runs / max(t_probe, 1e-9))))
+    b = 1 << (b.bit_length() - 1)                             # power of two <= b
+    x, w = make_inputs(dict(cfg, x=(b, *cfg["x"][1:])))
+    for _ in range(warmup):
+        step(x, w, cfg)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step(x, w, cfg)
+        times.append(time.perf_counter() - t0)
+    return kind, b, times
+
+
+def run_reference(args, cfg, name):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    kind, b, times = cpu_sample(cfg, budget_s=90.0, steps=args.steps, warmup=args.warmup)
+    ms = 1e3 * float(np.mean(times))
+    v = b / (ms * 1e-3)
+    cores = host_threads()
+    sample = f"batch {b} of {cfg['x'][0]} (same layer), mean of {args.steps} steps after {args.warmup} warm-up"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+        "config": {"workload": workload_name(name, cfg), "host": "NumPy/OpenBLAS on the box's CPU cores"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm ---------------------------------------------------------------------------------
+
+def run_ours(args, cfg, name):
+    import mygrad_b200 as mg
+    from mygrad_b200 import Tensor
+    from mygrad_b200._lib import check, lib
+    from mygrad_b200.dist import DataParallel
+    from mygrad_b200.nnet.layers import conv_nd, max_pool
+    from mygrad_b200.nnet.layers.conv import ConvND
+    from mygrad_b200.nnet.layers.pooling import MaxPoolND
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dp = DataParallel(rank, world, local).init()
+
+    def barrier():
+        mg.synchronize()
+        if dist is not None:
+            dist.barrier()
+        mg.synchronize()
+
+    geo = geometry(cfg)
+    dt = NP_DTYPE[cfg["dtype"]]
+    xh, wh = make_inputs(cfg)
+    x_dev, w_dev = mg.asdevice(xh), mg.asdevice(wh)
+    conv_kw = dict(stride=cfg["stride"], padding=cfg["padding"], dilation=cfg["dilation"])
+
+    def step(xd, wd):
+        xt, wt = Tensor(xd, copy=False), Tensor(wd, copy=False)
+        y = conv_nd(xt, wt, **conv_kw)
+        o = max_pool(y, cfg["pool"], 2) if cfg["pool"] else y
+        o.backward()
+        if world > 1:
+            dp.allreduce([wt.grad])
+        return o, xt, wt
+
+    def events():
+        a, b = C.c_void_p(), C.c_void_p()
+        check(lib.mgb_event_create(C.byref(a))); check(lib.mgb_event_create(C.byref(b)))
+        return a, b
+
+    def elapsed(a, b) -> float:
+        ms = C.c_float(0)
+        check(lib.mgb_event_synchronize(b))
+        check(lib.mgb_event_elapsed_ms(a, b, C.byref(ms)))
+        return float(ms.value)
+
+    stream = C.c_void_p(mg.current_stream())
+
+    def max_over_ranks(v: float) -> float:
+        if dist is None:
+            return v
+        import torch
+
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput -----------------------------------------------------
+    for _ in range(args.warmup):
+        step(x_dev, w_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0, n1 = C.c_uint64(0), C.c_uint64(0)
+    lib.mgb_launch_count(C.byref(n0))
+    e0, e1 = events()
+    check(lib.mgb_event_record(e0, stream))
+    for _ in range(args.steps):
+        step(x_dev, w_dev)
+    check(lib.mgb_event_record(e1, stream))
+    total_ms = elapsed(e0, e1)
+    barrier()
+    lib.mgb_launch_count(C.byref(n1))
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    batch = cfg["x"][0]
+    value = world * batch / (ms_per_step * 1e-3)
+
+    # ---- end to end with host buffers ------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        px, pw = mg.pinned_empty(cfg["x"], dt), mg.pinned_empty(cfg["w"], dt)
+        px[...] = xh; pw[...] = wh
+        o, xt, wt = step(x_dev, w_dev)
+        po = mg.pinned_empty(o.shape, dt)
+        pdx, pdw = mg.pinned_empty(cfg["x"], dt), mg.pinned_empty(cfg["w"], dt)
+        xd2, wd2 = mg.empty(cfg["x"], dt), mg.empty(cfg["w"], dt)
+
+        def e2e_step():
+            xd2.set_from_host(px, sync=False)
+            wd2.set_from_host(pw, sync=False)
+            o, xt, wt = step(xd2, wd2)
+            o.data.get(po, sync=False)
+            xt.grad.get(pdx, sync=False)
+            wt.grad.get(pdw, sync=False)
+            mg.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        ke = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            e2e_step()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / ke)
+        e2e = {"value": world * batch / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(px.nbytes + pw.nbytes),
+               "d2h_bytes_per_step": int(po.nbytes + pdx.nbytes + pdw.nbytes)}
+
+    # ---- per-phase timing: which kernel dominates, and its roofline -------------------------
+    # (straight through the C ABI with preallocated outputs, so that only kernels are timed)
+    phases = {}
+    if rank == 0:
+        from mygrad_b200._lib import ConvDesc, PoolDesc
+
+        nd = len(cfg["x"]) - 2
+        tup = lambda v: (v,) * nd if isinstance(v, int) else tuple(v)
+        cd = ConvDesc()
+        cd.dtype, cd.nd = (0 if cfg["dtype"] == "f32" else 1), nd
+        cd.N, cd.C, cd.F = cfg["x"][0], cfg["x"][1], cfg["w"][0]
+        for i in range(nd):
+            cd.X[i], cd.W[i] = cfg["x"][2 + i], cfg["w"][2 + i]
+            cd.stride[i], cd.pad[i], cd.dil[i] = tup(cfg["stride"])[i], tup(cfg["padding"])[i], tup(cfg["dilation"])[i]
+        y = mg.empty((cfg["x"][0], cfg["w"][0], *geo["G"]), dt)
+        gy = mg.full(y.shape, 1.0, dt)
+        dx, dw = mg.empty(cfg["x"], dt), mg.empty(cfg["w"], dt)
+        wss = []
+        for which in range(3):
+            n = C.c_size_t(0)
+            check(lib.mgb_conv_workspace_bytes(C.byref(cd), which, C.byref(n)))
+            wss.append((mg.empty((max(8, n.value) + 7) // 8, np.float64), n.value))
+        P = lambda a: C.c_void_p(a.ptr)
+
+        def timed(fn, reps=5):
+            fn()
+            a, b = events()
+            check(lib.mgb_event_record(a, stream))
+            for _ in range(reps):
+                fn()
+            check(lib.mgb_event_record(b, stream))
+            return elapsed(a, b) / reps
+
+        phases["conv_fwd"] = {"ms": timed(lambda: check(lib.mgb_conv_fwd(
+            C.byref(cd), P(x_dev), P(w_dev), P(y), P(wss[0][0]), wss[0][1], stream))), "flops": geo["flops"]}
+        if cfg["pool"]:
+            npool = len(cfg["pool"])
+            pd = PoolDesc()
+            pd.dtype, pd.nd, pd.mode = cd.dtype, npool, 0
+            pd.lead = int(np.prod(y.shape[: y.ndim - npool]))
+            for i in range(npool):
+                pd.X[i], pd.P[i], pd.stride[i] = y.shape[y.ndim - npool + i], cfg["pool"][i], 2
+            pooled = mg.empty((*y.shape[: y.ndim - npool],
+                               *[(X - p_) // 2 + 1 for X, p_ in zip(y.shape[y.ndim - npool:], cfg["pool"])]), dt)
+            gp = mg.full(pooled.shape, 1.0, dt)
+            phases["pool_fwd"] = {"ms": timed(lambda: check(lib.mgb_pool_fwd(C.byref(pd), P(y), P(pooled), stream))),
+                                  "bytes": geo["y_bytes"] + geo["p_bytes"]}
+            phases["pool_bwd"] = {"ms": timed(lambda: check(lib.mgb_pool_bwd(C.byref(pd), P(gp), P(y), P(gy), stream))),
+                                  "bytes": 2 * geo["y_bytes"] + geo["p_bytes"]}
+        phases["conv_dgrad"] = {"ms": timed(lambda: check(lib.mgb_conv_dgrad(
+            C.byref(cd), P(gy), P(w_dev), P(dx), P(wss[1][0]), wss[1][1], stream))), "flops": geo["flops"]}
+        phases["conv_wgrad"] = {"ms": timed(lambda: check(lib.mgb_conv_wgrad(
+            C.byref(cd), P(gy), P(x_dev), P(dw), P(wss[2][0]), wss[2][1], stream))), "flops": geo["flops"]}
+
+    # ---- measured ceilings -----------------------------------------------------------------------
+    peaks = {}
+    mp_file = ROOT / "MEASURED_PEAKS.json"
+    measured = json.loads(mp_file.read_text()) if mp_file.exists() else {}
+    hbm_peak = measured.get("hbm_gbs", 6650.0)
+    bf16_peak = measured.get("bf16_tflops_sustained", measured.get("bf16_tflops", 1590.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if measured else "fallback (B200_PROFILING.md)"
+    if rank == 0:
+        tf = C.c_double(0)
+        check(lib.mgb_probe_mma_peak(0, 4096, C.byref(tf), stream)); peaks["fp64_dmma_tflops"] = tf.value
+        check(lib.mgb_probe_mma_peak(1, 4096, C.byref(tf), stream)); peaks["tf32_mma_sync_tflops"] = tf.value
+        peaks["hbm_gbs"] = hbm_peak
+        peaks["bf16_tflops"] = bf16_peak
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        kind, b, times = cpu_sample(cfg, budget_s=20.0)
+        cpu = {"value": b / times[0], "unit": "samples/s", "cores": host_threads(), "kind": kind,
+               "sample": f"batch {b} of {batch} (same layer), one timed step after a 2-sample probe"}
+
+    if rank == 0:
+        top = max(phases, key=lambda k: phases[k]["ms"])
+        ph = phases[top]
+        if "flops" in ph:
+            achieved = ph["flops"] / (ph["ms"] * 1e-3) / 1e12
+            if cfg["dtype"] == "f64":
+                peak, basis = peaks["fp64_dmma_tflops"], "FP64 DMMA register-resident loop measured in this run (mgb_probe_mma_peak)"
+            else:
+                peak = bf16_peak / 2.0 / 3.0
+                basis = (f"{peak_src} bf16 sustained {bf16_peak} TF/s / 2 (TF32 runs at half the bf16 rate) "
+                         "/ 3 (3xTF32: three MMAs per fp32 product)")
+            roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "peak_basis": basis}
+        else:
+            achieved = ph["bytes"] / (ph["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_basis": peak_src}
+        for k, v in phases.items():
+            if "flops" in v:
+                v["tflops"] = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            else:
+                v["gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "config": {"workload": workload_name(name, cfg), "per_gpu_batch": batch,
+                       "parallelism": f"dp{world} (batch shards, dW all-reduce)" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (x+y+dy > 126 MB), no flush between steps"
+                             if geo["x_bytes"] + 2 * geo["y_bytes"] > 126e6 else "working set fits L2; not flushed"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(n1.value - n0.value),
+            "roofline": roof, "cpu_baseline": cpu, "phases": phases, "peaks": peaks,
+        }
+        print(json.dumps(line), flush=True)
+    barrier()
+    dp.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg, args.workload)
+    else:
+        run_ours(args, cfg, args.workload)
+
+
+if __name__ == "__main__":
+    main()

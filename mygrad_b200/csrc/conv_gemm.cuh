@@ -220,15 +220,20 @@ __device__ __forceinline__ void mma_slab(const T* __restrict__ As, const T* __re
         split_tf32(Bs[n * C::LDK + k0], bhi[j][0], blo[j][0]);
         split_tf32(Bs[n * C::LDK + k1], bhi[j][1], blo[j][1]);
       }
-      // small cross terms first, the hi*hi product last
+      // small cross terms first, the hi*hi product last.  Three separate sweeps keep the
+      // dependent MMAs on one accumulator MI*NI issues apart (mma.sync latency ~30 cycles).
 #pragma unroll
       for (int i = 0; i < C::MI; ++i)
 #pragma unroll
-        for (int j = 0; j < C::NI; ++j) {
-          mma_tf32_16x8x8(accf[i][j], alo[i], bhi[j]);
-          mma_tf32_16x8x8(accf[i][j], ahi[i], blo[j]);
-          mma_tf32_16x8x8(accf[i][j], ahi[i], bhi[j]);
-        }
+        for (int j = 0; j < C::NI; ++j) mma_tf32_16x8x8(accf[i][j], alo[i], bhi[j]);
+#pragma unroll
+      for (int i = 0; i < C::MI; ++i)
+#pragma unroll
+        for (int j = 0; j < C::NI; ++j) mma_tf32_16x8x8(accf[i][j], ahi[i], blo[j]);
+#pragma unroll
+      for (int i = 0; i < C::MI; ++i)
+#pragma unroll
+        for (int j = 0; j < C::NI; ++j) mma_tf32_16x8x8(accf[i][j], ahi[i], bhi[j]);
     }
   }
 }

@@ -86,6 +86,8 @@ class DeviceArray:
 
     def __init__(self, shape: Sequence[int], dtype=np.float32, *, _alloc=None, _ptr=None,
                  _keepalive=None, _base=None):
+        if isinstance(shape, (int, np.integer)):
+            shape = (shape,)
         self.shape: Tuple[int, ...] = tuple(int(s) for s in shape)
         self.dtype = np.dtype(dtype)
         if self.dtype not in _SUPPORTED:

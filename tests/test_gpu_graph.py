@@ -1,0 +1,214 @@
+"""Tensor.backward / Operation.backward semantics on device buffers, and the raw C ABI
+driven with foreign (torch) buffers through __cuda_array_interface__."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import mygrad_b200 as mg
+from conftest import assert_close
+from mygrad_b200 import DeviceArray, InvalidBackprop, InvalidGradient, Operation, Tensor
+from mygrad_b200._lib import ConvDesc, PoolDesc, check, lib
+from mygrad_b200.nnet.layers import conv_nd, max_pool
+from oracle import conv_pool_oracle as oc
+
+pytestmark = pytest.mark.gpu
+
+
+class Add(Operation):
+    """a + b with NumPy broadcasting; backward_var hands `grad` itself back, exactly like
+    mygrad's Add (math/arithmetic/ops.py:28-32) — Operation.backward must copy and un-broadcast."""
+
+    def __call__(self, a, b):
+        self.variables = (a, b)
+        out = (a.data.get().astype(np.result_type(a.dtype, b.dtype)) + b.data.get())
+        return mg.asdevice(out)
+
+    def backward_var(self, grad, index, **kwargs):
+        return grad
+
+
+def add(a, b):
+    return Tensor._op(Add, a, b)
+
+
+def test_multi_consumer_accumulation_vs_golden(graph_golden):
+    c = graph_golden.case("acc")
+    x, w1, w2 = Tensor(c["x"]), Tensor(c["w1"]), Tensor(c["w2"])
+    total = add(conv_nd(x, w1, stride=1, padding=1), conv_nd(x, w2, stride=1, padding=1))
+    o = max_pool(total, (2, 2), 2)
+    o.backward()
+    assert_close(o.numpy(), c["out"])
+    assert_close(total.grad.get(), c["dtotal"])
+    assert_close(x.grad.get(), c["dx"])          # two arrivals: first copy, then `+=`
+    assert_close(w1.grad.get(), c["dw1"])
+    assert_close(w2.grad.get(), c["dw2"])
+
+
+def test_bias_unbroadcast_vs_golden(graph_golden):
+    c, a = graph_golden.case("bias"), graph_golden.case("acc")
+    x, w1 = Tensor(a["x"]), Tensor(a["w1"])
+    b4, b3 = Tensor(c["b4"]), Tensor(c["b3"])
+    y = add(add(conv_nd(x, w1, stride=1, padding=1), b4), b3)
+    y.backward(c["g"])
+    assert_close(y.numpy(), c["y"])
+    assert b4.grad.shape == (1, 3, 1, 1) and b3.grad.shape == (3, 1, 1)
+    assert_close(b4.grad.get(), c["db4"])
+    assert_close(b3.grad.get(), c["db3"])
+    assert_close(x.grad.get(), c["dx"])
+
+
+def test_reduce_broadcast_shapes_vs_golden(graph_golden):
+    n = int(graph_golden.npz["rb_count"])
+    for i in range(n):
+        c = graph_golden.case(f"rb{i}")
+        vshape = tuple(int(v) for v in c["vshape"])
+        for dt in (np.float64, np.float32):
+            out = Operation.grad_post_process_fn(mg.asdevice(c["g"].astype(dt)), vshape)
+            assert out.shape == vshape
+            assert_close(out.get(), c["out"].astype(dt), dt, err_msg=f"{c['g'].shape}->{vshape}")
+    with pytest.raises(ValueError):
+        Operation.grad_post_process_fn(mg.asdevice(np.ones((3,))), (2, 3))
+
+
+def test_reduce_broadcast_large_bias_shape():
+    # config-5-like bias grad (N,F,H,W) -> (1,F,1,1): many rows per output, split across CTAs
+    rng = np.random.default_rng(3)
+    g = rng.standard_normal((64, 32, 32, 32)).astype(np.float32)
+    out = mg.asdevice(g).sum_to_shape((1, 32, 1, 1)).get()
+    want = g.astype(np.float64).sum(axis=(0, 2, 3), keepdims=True)
+    np.testing.assert_allclose(out, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+    out2 = mg.asdevice(g.reshape(64 * 32, 1024)).sum_to_shape((1024,)).get()
+    np.testing.assert_allclose(out2, g.reshape(-1, 1024).astype(np.float64).sum(0), rtol=1e-5, atol=1e-3)
+
+
+def test_pool_grad_dtype_follows_x(graph_golden):
+    c = graph_golden.case("pool32")
+    x = Tensor(c["x"])
+    o = max_pool(x, (3, 3), 2)
+    o.backward(c["g"])
+    assert x.grad.dtype == np.float32            # float64 scatter buffer, cast back (operation_base.py:223-224)
+    np.testing.assert_array_equal(x.grad.get(), c["dx"])
+
+
+def test_backward_seed_and_graph_clearing():
+    # tests/tensor_base/test_backward.py:21-96, test_no_null_grad_semantics.py:19-36,
+    # test_backprop_through_non_scalar.py:11-18
+    rng = np.random.default_rng(0)
+    xh, wh = rng.standard_normal((2, 2, 6, 6)), rng.standard_normal((3, 2, 3, 3))
+    x, w = Tensor(xh), Tensor(wh)
+    y = conv_nd(x, w, stride=1)
+    y.backward()                                  # non-scalar terminal == sum().backward()
+    assert y.grad.dtype == y.dtype
+    np.testing.assert_array_equal(y.grad.get(), np.ones(y.shape))
+    assert_close(w.grad.get(), oc.conv_dw(np.ones(y.shape), xh, wh.shape, 1))
+    assert y.creator is None and not x._ops and not w._ops
+    first = x.grad
+    y2 = conv_nd(x, w, stride=1)                  # re-use nulls the grads of the inputs
+    assert x.grad is None and w.grad is None and first is not None
+    y2.backward(2.0)                              # scalar grad broadcasts
+    np.testing.assert_array_equal(y2.grad.get(), np.full(y2.shape, 2.0))
+    assert_close(x.grad.get(), 2 * oc.conv_dx(np.ones(y.shape), xh.shape, wh, 1))
+    y3 = conv_nd(x, w, stride=1)
+    with pytest.raises(ValueError):
+        y3.backward(np.ones((5,)))                # not broadcast-compatible
+    y3.clear_graph()
+    xf = Tensor(xh.astype(np.float32))
+    y4 = conv_nd(xf, w, stride=1)                 # f32 x, f64 w -> f64 y, x.grad f32, w.grad f64
+    y4.backward(np.ones(y4.shape, dtype=np.float32))
+    assert (y4.dtype, xf.grad.dtype, w.grad.dtype) == (np.float64, np.float32, np.float64)
+
+
+def test_constants_and_no_autodiff():
+    rng = np.random.default_rng(1)
+    xh, wh = rng.standard_normal((1, 2, 5, 5)), rng.standard_normal((2, 2, 2, 2))
+    x, w = Tensor(xh, constant=True), Tensor(wh)
+    y = conv_nd(x, w, stride=1)
+    assert y.constant is False
+    y.backward()
+    assert x.grad is None and w.grad is not None  # constants are skipped (operation_base.py:179)
+    yc = conv_nd(xh, wh, stride=1)                # bare arrays become constant tensors
+    assert yc.constant is True
+    yc.backward()
+    assert yc.grad is None
+    with mg.no_autodiff:
+        yn = conv_nd(Tensor(xh), w, stride=1)
+        assert yn.creator is None
+        yn.backward()
+        assert yn.grad is None
+    assert_close(yn.numpy(), oc.conv_fwd(xh, wh, 1))
+
+
+def test_invalid_backprop_and_invalid_gradient():
+    class Bad(Operation):
+        def __call__(self, a):
+            self.variables = (a,)
+            return a.data.copy()
+
+        def backward_var(self, grad, index, **kwargs):
+            return "not a gradient"
+
+    x = Tensor(np.ones((2, 2)))
+    with pytest.raises(InvalidGradient):
+        Tensor._op(Bad, x).backward()             # tests/test_operation_base.py:15-57
+
+    x = Tensor(np.ones((1, 1, 4, 4)))
+    y = conv_nd(x, np.ones((1, 1, 2, 2)), stride=1)
+    z = max_pool(y, (3, 3), 1)
+    y.clear_graph()                               # z's creator still points at the cleared y
+    with pytest.raises(InvalidBackprop):
+        z.backward()
+
+
+# ---- raw C ABI with foreign buffers ---------------------------------------------------------
+
+def test_c_abi_with_torch_buffers():
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(4)
+    xh = rng.standard_normal((3, 4, 9, 9)).astype(np.float32)
+    wh = rng.standard_normal((5, 4, 3, 3)).astype(np.float32)
+    xt, wt = torch.from_numpy(xh).to(dev), torch.from_numpy(wh).to(dev)
+    yt = torch.empty((3, 5, 9, 9), device=dev)
+    d = ConvDesc()
+    d.dtype, d.nd, d.N, d.C, d.F = 0, 2, 3, 4, 5
+    for i in range(2):
+        d.X[i], d.W[i], d.stride[i], d.pad[i], d.dil[i] = 9, 3, 1, 1, 1
+    n = C.c_size_t(0)
+    check(lib.mgb_conv_workspace_bytes(C.byref(d), 0, C.byref(n)))
+    ws = torch.empty(n.value, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    check(lib.mgb_conv_fwd(C.byref(d), C.c_void_p(xt.data_ptr()), C.c_void_p(wt.data_ptr()),
+                           C.c_void_p(yt.data_ptr()), C.c_void_p(ws.data_ptr()), n, None))
+    check(lib.mgb_device_synchronize())
+    assert_close(yt.cpu().numpy(), oc.conv_fwd(xh, wh, 1, 1, 1), np.float32)
+    # too-small workspace is an error status, not a crash
+    assert lib.mgb_conv_fwd(C.byref(d), C.c_void_p(xt.data_ptr()), C.c_void_p(wt.data_ptr()),
+                            C.c_void_p(yt.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_size_t(8), None) != 0
+    assert b"workspace" in lib.mgb_last_error()
+    # zero-copy import of a torch tensor through __cuda_array_interface__, and export back
+    t = Tensor(xt, copy=False)
+    assert t.data.ptr == xt.data_ptr()
+    out = max_pool(t, (3, 3), 3)
+    back = torch.as_tensor(out.data, device=dev)
+    np.testing.assert_array_equal(back.cpu().numpy(), oc.max_pool_fwd(xh, (3, 3), 3))
+    # torch's own conv as an independent third opinion (not part of the reference)
+    ref = torch.nn.functional.conv2d(xt.double(), wt.double(), padding=1).float().cpu().numpy()
+    assert_close(yt.cpu().numpy(), ref, np.float32)
+
+
+def test_pool_c_abi_rejects_bad_descriptor():
+    d = PoolDesc()
+    d.dtype, d.nd, d.mode, d.lead = 0, 2, 0, 1
+    d.X[0], d.X[1], d.P[0], d.P[1], d.stride[0], d.stride[1] = 5, 5, 2, 2, 2, 2
+    buf = mg.empty((25,), np.float32)
+    assert lib.mgb_pool_fwd(C.byref(d), C.c_void_p(buf.ptr), C.c_void_p(buf.ptr), None) != 0
+    assert b"incompatible" in lib.mgb_last_error()
+
+
+def test_launch_counter_counts_kernels():
+    before, after = C.c_uint64(0), C.c_uint64(0)
+    lib.mgb_launch_count(C.byref(before))
+    mg.full((1024,), 1.0, np.float32)
+    lib.mgb_launch_count(C.byref(after))
+    assert after.value == before.value + 1

@@ -1,0 +1,288 @@
+"""Parity of the CUDA path with the reference, through the public API
+(conv_nd / max_pool / Tensor.backward -> ctypes -> libmgb200.so).
+
+Checks, in order: the reference's by-hand known answers, the golden vectors generated
+from the live reference, seeded random cases against the oracle, and — at BASELINE.json's
+full sizes — size-independent properties plus spot checks of single samples.
+Tolerances are the north star's: pooling bit-exact, conv rtol 1e-10 (f64) / 1e-5 (f32).
+"""
+import numpy as np
+import pytest
+
+import mygrad_b200 as mg
+from conftest import GoldenFile, assert_close
+from mygrad_b200 import Tensor
+from mygrad_b200.nnet.layers import conv_nd, max_pool, mean_pool
+from oracle import conv_pool_oracle as oc
+from test_oracle import POOL_KNOWN
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- known answers pinned by the reference's own tests -------------------------------
+
+def test_conv_known_answers():
+    # tests/nnet/layers/test_conv.py:179-217
+    x = Tensor(np.arange(1, 5).reshape(1, 1, 4).astype(float))
+    k = Tensor(-1 * np.arange(1, 3).reshape(1, 1, 2).astype(float))
+    o = conv_nd(x, k, stride=(2,), constant=True)
+    assert isinstance(o, Tensor) and o.constant is True
+    np.testing.assert_allclose(o.numpy(), [[[-5.0, -11.0]]])
+    x = Tensor(np.arange(1, 13).reshape(1, 1, 3, 4).astype(float))
+    k = Tensor(-1 * np.arange(1, 5).reshape(1, 1, 2, 2).astype(float))
+    o = conv_nd(Tensor(x), k, stride=(1, 2), constant=True)
+    np.testing.assert_allclose(o.numpy(), [[[[-44.0, -64.0], [-84.0, -104.0]]]])
+
+
+def test_conv_docstring_example():
+    # src/mygrad/nnet/layers/conv.py:251-264
+    xh = np.zeros((1, 1, 16), dtype=np.float32)
+    xh[..., 5:11] = 1
+    x, k = Tensor(xh), Tensor(np.ones((1, 1, 5), dtype=np.float32))
+    y = conv_nd(x, k, stride=1)
+    assert y.dtype == np.float32
+    np.testing.assert_allclose(y.numpy()[0, 0], [0, 1, 2, 3, 4, 5, 5, 4, 3, 2, 1, 0])
+    y.backward()
+    np.testing.assert_allclose(x.grad.get()[0, 0], [1, 2, 3, 4, 5, 5, 5, 5, 5, 5, 5, 5, 4, 3, 2, 1])
+    np.testing.assert_allclose(k.grad.get()[0, 0], [6, 6, 6, 6, 6])
+    assert conv_nd(np.zeros((10, 3, 32, 32)), np.zeros((5, 3, 2, 2)), stride=2).shape == (10, 5, 16, 16)
+
+
+@pytest.mark.parametrize("case", range(len(POOL_KNOWN)))
+def test_pool_known_answers(case):
+    # tests/nnet/layers/test_maxpool.py:33-178
+    xh, pool, stride, gkind, fwd, bwd = POOL_KNOWN[case]
+    x = Tensor(xh, dtype="float32")
+    out = max_pool(x, pool, stride)
+    g = np.arange(out.size).reshape(out.shape) if gkind == "arange" else None
+    out.backward(g)
+    np.testing.assert_array_equal(out.numpy(), np.array(fwd, dtype=np.float32))
+    assert x.grad.dtype == np.float32
+    np.testing.assert_array_equal(x.grad.get(), np.array(bwd, dtype=np.float32))
+    assert max_pool(x, pool, stride, constant=True).constant is True
+    assert max_pool(x, pool, stride, constant=False).constant is False
+
+
+def test_pool_docstring_example():
+    # src/mygrad/nnet/layers/pooling.py:203-214
+    x = Tensor([[0.0, 10.0, 8.0], [9.0, 7.0, 3.0], [5.0, 0.0, 20.0]])
+    out = max_pool(x, pool=(2,), stride=1)
+    np.testing.assert_array_equal(out.numpy(), [[10, 10], [9, 7], [5, 20]])
+    out.backward()
+    np.testing.assert_array_equal(x.grad.get(), [[0, 2, 0], [1, 1, 0], [1, 0, 1]])
+    assert max_pool(np.random.rand(10, 3, 12, 12), (2, 2), (2, 1)).shape == (10, 3, 6, 11)
+
+
+def test_padding_only_input_gives_exact_zero():
+    # tests/nnet/layers/test_conv.py:247-273
+    for nd, padding in ((1, 2), (2, (1, 3)), (3, 1)):
+        pads = (padding,) * nd if isinstance(padding, int) else padding
+        x = Tensor(np.zeros((1, 1) + (0,) * nd))
+        k = np.random.default_rng(0).standard_normal((1, 1) + tuple(2 * p for p in pads))
+        out = conv_nd(x, k, padding=padding, stride=1)
+        assert out.shape == (1,) * x.ndim
+        assert out.item() == 0.0
+        out.backward()
+        assert x.grad.shape == x.shape
+
+
+# ---- golden vectors generated from the live reference ---------------------------------
+
+@pytest.mark.parametrize("name", GoldenFile("conv_cases.npz").names())
+def test_conv_vs_golden(name, conv_golden):
+    c, m = conv_golden.case(name), conv_golden.manifest[name]
+    x, w = Tensor(c["x"]), Tensor(c["w"])
+    y = conv_nd(x, w, stride=m["stride"], padding=m["padding"], dilation=m["dilation"])
+    assert y.shape == c["y"].shape and y.dtype == c["y"].dtype
+    y.backward(c["g"])
+    assert_close(y.numpy(), c["y"], c["y"].dtype, err_msg=name)
+    assert x.grad.dtype == c["dx"].dtype and w.grad.dtype == c["dw"].dtype
+    assert_close(x.grad.get(), c["dx"], c["dx"].dtype, err_msg=name + " dx")
+    assert_close(w.grad.get(), c["dw"], c["dw"].dtype, err_msg=name + " dw")
+    assert y.creator is None and not x._ops      # graph cleared after backward
+
+
+@pytest.mark.parametrize("name", GoldenFile("pool_cases.npz").names())
+def test_pool_vs_golden_bit_exact(name, pool_golden):
+    c, m = pool_golden.case(name), pool_golden.manifest[name]
+    x = Tensor(c["x"])
+    y = max_pool(x, tuple(m["pool"]), m["stride"])
+    y.backward(c["g"])
+    np.testing.assert_array_equal(y.numpy(), c["y"], err_msg=name)
+    assert x.grad.dtype == c["x"].dtype
+    np.testing.assert_array_equal(x.grad.get(), c["dx"], err_msg=name + " dx")
+    # mean-pool: composed definition (parity unpinned by the reference)
+    xm = Tensor(c["x"])
+    ym = mean_pool(xm, tuple(m["pool"]), m["stride"])
+    rtol = 1e-10 if c["x"].dtype == np.float64 else 1e-5
+    np.testing.assert_allclose(ym.numpy(), c["mean"], rtol=rtol, atol=rtol, equal_nan=True, err_msg=name)
+    if np.isfinite(c["x"]).all():
+        ym.backward(c["g"])
+        want = oc.mean_pool_bwd(c["g"], c["x"].shape, m["pool"], m["stride"])
+        np.testing.assert_allclose(xm.grad.get(), want, rtol=rtol, atol=rtol, err_msg=name)
+
+
+@pytest.mark.parametrize("name", GoldenFile("layer_cases.npz").names())
+def test_layer_vs_golden(name, layer_golden):
+    c, m = layer_golden.case(name), layer_golden.manifest[name]
+    x, w = Tensor(c["x"]), Tensor(c["w"])
+    y = conv_nd(x, w, stride=m["stride"], padding=m["padding"], dilation=m["dilation"])
+    o = max_pool(y, tuple(m["pool"]), m["pool_stride"]) if m["pool"] else y
+    o.backward()
+    dt = c["x"].dtype
+    assert_close(o.numpy(), c["out"], dt, err_msg=name)
+    assert_close(y.grad.get(), c["dconv"], dt, err_msg=name + " intermediate grad is kept")
+    assert_close(x.grad.get(), c["dx"], dt, err_msg=name)
+    assert_close(w.grad.get(), c["dw"], dt, err_msg=name)
+
+
+# ---- seeded random cases against the oracle ---------------------------------------------
+
+def _random_conv_case(rng, nd, dtype):
+    W = tuple(int(rng.integers(1, 4)) for _ in range(nd))
+    d = tuple(int(rng.integers(1, 3)) for _ in range(nd))
+    s = tuple(int(rng.integers(1, 4)) for _ in range(nd))
+    p = tuple(int(rng.integers(0, 3)) for _ in range(nd))
+    G = tuple(int(rng.integers(1, 7 if nd < 3 else 4)) for _ in range(nd))
+    X = tuple((g - 1) * si + (wi - 1) * di + 1 - 2 * pi for g, si, wi, di, pi in zip(G, s, W, d, p))
+    if any(xi < 0 for xi in X):
+        return None
+    N, C, F = int(rng.integers(1, 4)), int(rng.integers(1, 6)), int(rng.integers(1, 6))
+    x = rng.standard_normal((N, C, *X)).astype(dtype)
+    w = rng.standard_normal((F, C, *W)).astype(dtype)
+    return x, w, s, p, d
+
+
+@pytest.mark.parametrize("nd", [1, 2, 3])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_conv_random_vs_oracle(nd, dtype):
+    # same space as tests/nnet/layers/test_conv.py:320-447 (1-3 spatial dims, random
+    # stride / dilation / padding); analytic gradients from the oracle replace complex-step
+    rng = np.random.default_rng(1000 + 10 * nd + (dtype == np.float32))
+    done = 0
+    while done < 25:
+        case = _random_conv_case(rng, nd, dtype)
+        if case is None:
+            continue
+        x, w, s, p, d = case
+        done += 1
+        xt, wt = Tensor(x), Tensor(w)
+        y = conv_nd(xt, wt, stride=s, padding=p, dilation=d)
+        want = oc.conv_fwd(x, w, s, p, d)
+        msg = f"x{x.shape} w{w.shape} s{s} p{p} d{d}"
+        assert y.shape == want.shape, msg
+        assert_close(y.numpy(), want, dtype, err_msg=msg)
+        g = rng.standard_normal(want.shape).astype(dtype)
+        y.backward(g)
+        assert_close(xt.grad.get(), oc.conv_dx(g, x.shape, w, s, p, d, dtype=dtype), dtype, err_msg=msg + " dx")
+        assert_close(wt.grad.get(), oc.conv_dw(g, x, w.shape, s, p, d), dtype, err_msg=msg + " dw")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_conv_tile_boundaries_vs_oracle(dtype):
+    """shapes chosen to straddle the 128/64/32-wide GEMM tiles and the K slabs"""
+    rng = np.random.default_rng(5)
+    for (N, C, F, X, W, s, p) in [(3, 7, 33, (11, 13), (3, 3), 1, 1), (2, 20, 65, (9, 9), (3, 3), 1, 1),
+                                  (5, 9, 129, (7, 6), (2, 2), 1, 0), (2, 17, 130, (13, 13), (3, 3), 2, 1),
+                                  (130, 3, 4, (5, 5), (3, 3), 1, 1)]:
+        x = rng.standard_normal((N, C, *X)).astype(dtype)
+        w = rng.standard_normal((F, C, *W)).astype(dtype)
+        xt, wt = Tensor(x), Tensor(w)
+        y = conv_nd(xt, wt, stride=s, padding=p)
+        want = oc.conv_fwd(x, w, s, p, 1)
+        assert_close(y.numpy(), want, dtype)
+        g = rng.standard_normal(want.shape).astype(dtype)
+        y.backward(g)
+        assert_close(xt.grad.get(), oc.conv_dx(g, x.shape, w, s, p, 1, dtype=dtype), dtype)
+        assert_close(wt.grad.get(), oc.conv_dw(g, x, w.shape, s, p, 1), dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_pool_random_vs_oracle_bit_exact(dtype):
+    rng = np.random.default_rng(77)
+    for _ in range(40):
+        nd = int(rng.integers(1, 4))
+        pool = tuple(int(rng.integers(1, 4)) for _ in range(nd))
+        stride = tuple(int(rng.integers(1, 4)) for _ in range(nd))
+        G = tuple(int(rng.integers(1, 6)) for _ in range(nd))
+        X = tuple((g - 1) * s + p for g, s, p in zip(G, stride, pool))
+        lead = tuple(int(rng.integers(1, 4)) for _ in range(int(rng.integers(0, 3))))
+        # small alphabet half of the time: ties exercise the first-max rule
+        if rng.integers(0, 2):
+            x = rng.integers(-2, 3, size=(*lead, *X)).astype(dtype)
+        else:
+            x = rng.standard_normal((*lead, *X)).astype(dtype)
+        xt = Tensor(x)
+        y = max_pool(xt, pool, stride)
+        np.testing.assert_array_equal(y.numpy(), oc.max_pool_fwd(x, pool, stride))
+        g = rng.standard_normal(y.shape).astype(dtype)
+        y.backward(g)
+        np.testing.assert_array_equal(xt.grad.get(), oc.max_pool_bwd(g, x, pool, stride).astype(dtype))
+
+
+# ---- BASELINE.json full sizes: properties + spot checks --------------------------------
+
+def _full_config(name):
+    if name == "C1":
+        return dict(x=(32, 3, 32, 32), w=(16, 3, 3, 3), s=1, p=1, d=1, pool=(2, 2), dt=np.float64)
+    if name == "C2":
+        return dict(x=(256, 64, 56, 56), w=(128, 64, 3, 3), s=1, p=1, d=1, pool=(2, 2), dt=np.float32)
+    if name == "C2f64":
+        return dict(x=(64, 64, 56, 56), w=(128, 64, 3, 3), s=1, p=1, d=1, pool=(2, 2), dt=np.float64)
+    if name == "C3":   # as written it is invalid; 65x65 is the nearest valid shape
+        return dict(x=(16, 128, 65, 65), w=(256, 128, 5, 5), s=2, p=0, d=2, pool=None, dt=np.float64)
+    if name == "C4":   # the per-GPU shard at 8 GPUs: 4 samples
+        return dict(x=(4, 32, 32, 64, 64), w=(64, 32, 3, 3, 3), s=1, p=0, d=1, pool=(2, 2, 2), dt=np.float32)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C2f64", "C3", "C4"])
+def test_full_size_spot_checks_and_properties(name):
+    cfg = _full_config(name)
+    dt = cfg["dt"]
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(cfg["x"]).astype(dt)
+    w = np.random.default_rng(1).standard_normal(cfg["w"]).astype(dt)
+    xt, wt = Tensor(x), Tensor(w)
+    y = conv_nd(xt, wt, stride=cfg["s"], padding=cfg["p"], dilation=cfg["d"])
+    out = max_pool(y, cfg["pool"], 2) if cfg["pool"] else y
+    out.backward()
+    yh, dxh, dwh = y.numpy(), xt.grad.get(), wt.grad.get()
+
+    # (1) spot check: two whole samples against the oracle (forward, pooling, dX)
+    for n in (0, cfg["x"][0] - 1):
+        xs = x[n:n + 1]
+        y_ref = oc.conv_fwd(xs, w, cfg["s"], cfg["p"], cfg["d"])
+        assert_close(yh[n:n + 1], y_ref, dt, err_msg=f"{name} fwd sample {n}")
+        if cfg["pool"]:
+            # pooling is exact on whatever y the GPU produced
+            np.testing.assert_array_equal(out.numpy()[n:n + 1], oc.max_pool_fwd(yh[n:n + 1], cfg["pool"], 2))
+            dy = oc.max_pool_bwd(np.ones(out.shape[1:], dt)[None], yh[n:n + 1], cfg["pool"], 2).astype(dt)
+            np.testing.assert_array_equal(y.grad.get()[n:n + 1], dy)
+        else:
+            dy = np.ones_like(y_ref)
+        dx_ref = oc.conv_dx(dy, xs.shape, w, cfg["s"], cfg["p"], cfg["d"], dtype=dt)
+        assert_close(dxh[n:n + 1], dx_ref, dt, err_msg=f"{name} dx sample {n}")
+
+    # (2) dW checksum: sum_n of per-sample oracle dW over a few samples, compared through
+    #     linearity: dW(full) - dW(without those samples) == dW(those samples)
+    keep = cfg["x"][0] // 2
+    x2, w2 = Tensor(x[:keep]), Tensor(w)
+    y2 = conv_nd(x2, w2, stride=cfg["s"], padding=cfg["p"], dilation=cfg["d"])
+    (max_pool(y2, cfg["pool"], 2) if cfg["pool"] else y2).backward()
+    x3, w3 = Tensor(x[keep:]), Tensor(w)
+    y3 = conv_nd(x3, w3, stride=cfg["s"], padding=cfg["p"], dilation=cfg["d"])
+    (max_pool(y3, cfg["pool"], 2) if cfg["pool"] else y3).backward()
+    assert_close(w2.grad.get() + w3.grad.get(), dwh, dt, err_msg=f"{name}: dW is additive over the batch")
+    np.testing.assert_array_equal(x2.grad.get(), dxh[:keep])   # dX is per-sample: bit-identical shards
+
+    # (3) adjoint identity <conv(x), g> == <x, dX(g)> == <w, dW(g)> for the all-ones-through-pool g
+    gy = y.grad.get().astype(np.float64)
+    lhs = float((yh.astype(np.float64) * gy).sum())
+    rtol = 1e-9 if dt == np.float64 else 2e-4
+    assert abs(lhs - float((x.astype(np.float64) * dxh).sum())) <= rtol * max(1.0, abs(lhs)), name
+    assert abs(lhs - float((w.astype(np.float64) * dwh).sum())) <= rtol * max(1.0, abs(lhs)), name
+
+    # (4) strided+dilated dX has exact zeros where no window lands (config 3)
+    if name == "C3":
+        assert np.all(dxh[..., 1::2, :] == 0) and np.all(dxh[..., :, 1::2] == 0)
