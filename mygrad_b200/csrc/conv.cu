@@ -3,7 +3,11 @@
 // tables (built on the device, in the caller's workspace) and launches.
 #include <vector>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "conv_gemm.cuh"
+#include "conv_tc.cuh"
 
 namespace mgb {
 namespace conv {
@@ -308,6 +312,205 @@ bool dgrad_needs_memset(const Plan& p, const std::vector<DgradClassPlan>& cls) {
   return covered != p.Xp;
 }
 
+// ---- FP32 on tcgen05 (conv_tc.cuh): planning ---------------------------------------------
+
+// MGB_CONV_F32_PATH=mma forces the mma.sync 3xTF32 kernels (A/B comparisons, fallback tests)
+bool tc_enabled() {
+  const char* e = getenv("MGB_CONV_F32_PATH");   // read per call: tests flip it at run time
+  return !(e && strcmp(e, "mma") == 0);
+}
+
+inline int round_up(long long v, int m) { return (int)((v + m - 1) / m * m); }
+
+// the tensor-core path wants a GEMM worth its fixed costs: >= 16 input and output channels
+bool tc_eligible(const Plan& p, int which) {
+  if (p.dtype != MGB_F32 || !tc_enabled()) return false;
+  long long cin = which == 0 ? p.C : p.F, cout = which == 0 ? p.F : p.C;
+  if (cin < 16 || cout < 16) return false;
+  if ((long long)round_up(cin, 32) * std::max(p.Xp, p.Gp) > INT32_MAX) return false;
+  return true;
+}
+
+struct TapBuild {          // taps of one GEMM: per-axis lists of (filter index, coordinate delta)
+  int cnt[3];
+  short kidx[3][kMaxW];
+  short delta[3][kMaxW];
+  int W[3];                // filter extents (to flatten kidx into the filter-bank tap index)
+  int X[3];                // source spatial extents
+  int cpad;
+};
+
+__global__ void build_tc_taps(tc::TcTap* taps, int* tap_list, TapBuild a) {
+  int ntap = a.cnt[0] * a.cnt[1] * a.cnt[2];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ntap; j += gridDim.x * blockDim.x) {
+    int t = j;
+    int j2 = t % a.cnt[2]; t /= a.cnt[2];
+    int j1 = t % a.cnt[1];
+    int j0 = t / a.cnt[1];
+    tc::TcTap e;
+    e.d0 = a.delta[0][j0]; e.d1 = a.delta[1][j1]; e.d2 = a.delta[2][j2];
+    e.off = (int)((((long long)e.d0 * a.X[1] + e.d1) * a.X[2] + e.d2) * a.cpad);
+    taps[j] = e;
+    tap_list[j] = (a.kidx[0][j0] * a.W[1] + a.kidx[1][j1]) * a.W[2] + a.kidx[2][j2];
+  }
+}
+
+struct TcLayout {          // workspace carve-up of one tensor-core GEMM
+  int cpad, bn, ny, rows, ntaps;
+  long long K;
+  size_t taps_off, list_off, bhi_off, blo_off, end;
+};
+
+TcLayout tc_layout(size_t start, long long cin, long long cout, int ntaps) {
+  TcLayout L;
+  L.cpad = round_up(cin, 32);
+  L.bn = std::min(128, round_up(cout, 16));
+  L.ny = (int)((cout + L.bn - 1) / L.bn);
+  L.rows = L.ny * L.bn;
+  L.ntaps = ntaps;
+  L.K = (long long)ntaps * L.cpad;
+  size_t off = align_up(start, 256);
+  L.taps_off = off; off += align_up((size_t)ntaps * sizeof(tc::TcTap), 256);
+  L.list_off = off; off += align_up((size_t)ntaps * sizeof(int), 256);
+  L.bhi_off = off;  off += align_up((size_t)L.rows * L.K * sizeof(float), 256);
+  L.blo_off = off;  off += align_up((size_t)L.rows * L.K * sizeof(float), 256);
+  L.end = off;
+  return L;
+}
+
+// channels-last hi/lo planes of the gathered tensor
+struct TcPlanes { size_t hi_off, lo_off, end; int cpad; };
+TcPlanes tc_planes(size_t start, long long n, long long chans, long long spatial) {
+  TcPlanes P;
+  P.cpad = round_up(chans, 32);
+  size_t bytes = align_up((size_t)n * spatial * P.cpad * sizeof(float), 1024);
+  P.hi_off = align_up(start, 1024);
+  P.lo_off = P.hi_off + bytes;
+  P.end = P.lo_off + bytes;
+  return P;
+}
+
+int tc_prep_planes(const float* src, float* hi, float* lo, long long n, long long chans,
+                   long long spatial, int cpad, cudaStream_t st) {
+  if (n * spatial == 0) return 0;
+  if (n > 65535) return fail("conv (tcgen05 path): batch %lld > 65535 unsupported", n);
+  dim3 grid((unsigned)((spatial + 31) / 32), (unsigned)(cpad / 32), (unsigned)n);
+  tc::nchw_to_nhwc_split<<<grid, 256, 0, st>>>(src, hi, lo, (int)chans, spatial, cpad);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc_launch(const tc::TcParams& tp, int ny, cudaStream_t st) {
+  constexpr int STAGES = 3;
+  size_t smem = tc::smem_bytes(tp.bn, STAGES);
+  MGB_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  dim3 grid((tp.M + tc::BM - 1) / tc::BM, ny);
+  tc::conv_tc_kernel<STAGES><<<grid, tc::THREADS, smem, st>>>(tp);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
+int pow2_cols(int bn) { int c = 32; while (c < bn) c <<= 1; return c; }
+
+size_t tc_fwd_ws(const Plan& p) {
+  TcPlanes P = tc_planes(0, p.N, p.C, p.Xp);
+  return tc_layout(P.end, p.C, p.F, (int)p.Wp).end;
+}
+
+int tc_fwd(const Plan& p, const float* x, const float* w, float* y, void* ws, size_t ws_bytes,
+           cudaStream_t st) {
+  long long M = p.N * p.Gp;
+  if (M * p.F == 0) return 0;
+  TcPlanes P = tc_planes(0, p.N, p.C, p.Xp);
+  TcLayout L = tc_layout(P.end, p.C, p.F, (int)p.Wp);
+  if (ws_bytes < L.end || !ws) return fail("conv fwd: workspace %zu < %zu bytes", ws_bytes, L.end);
+  char* base = (char*)ws;
+  float *ahi = (float*)(base + P.hi_off), *alo = (float*)(base + P.lo_off);
+  float *bhi = (float*)(base + L.bhi_off), *blo = (float*)(base + L.blo_off);
+  tc::TcTap* taps = (tc::TcTap*)(base + L.taps_off);
+  int* list = (int*)(base + L.list_off);
+  if (tc_prep_planes(x, ahi, alo, p.N, p.C, p.Xp, P.cpad, st)) return 1;
+  TapBuild tb;
+  for (int i = 0; i < 3; ++i) {
+    tb.cnt[i] = p.W[i]; tb.W[i] = p.W[i]; tb.X[i] = p.X[i];
+    for (int k = 0; k < p.W[i]; ++k) { tb.kidx[i][k] = (short)k; tb.delta[i][k] = (short)(k * p.D[i]); }
+  }
+  tb.cpad = P.cpad;
+  build_tc_taps<<<1, 256, 0, st>>>(taps, list, tb);
+  MGB_LAUNCH_CHECK();
+  tc::PackArgs pa{L.rows, L.cpad, (int)p.F, (int)p.C, (int)p.Wp, L.ntaps, 0};
+  tc::pack_filters_split<<<small_grid((long long)L.rows * L.K), 256, 0, st>>>(w, list, bhi, blo, pa);
+  MGB_LAUNCH_CHECK();
+  tc::TcParams tp;
+  tp.a_hi = ahi; tp.a_lo = alo; tp.taps = taps; tp.b_hi = bhi; tp.b_lo = blo; tp.out = y;
+  tp.om.sample_stride = p.F * p.Gp; tp.om.chan_stride = p.Gp;
+  for (int i = 0; i < 3; ++i) {
+    tp.om.omul[i] = 1; tp.om.obase[i] = 0;
+    tp.g.P[i] = p.G[i]; tp.g.pmul[i] = p.S[i]; tp.g.base[i] = -p.Pd[i]; tp.g.X[i] = p.X[i];
+  }
+  tp.om.os[2] = 1; tp.om.os[1] = p.G[2]; tp.om.os[0] = p.G[1] * p.G[2];
+  tp.g.sample_stride = p.Xp * P.cpad; tp.g.pp = (int)p.Gp; tp.g.cpad = P.cpad;
+  tp.g.nchunk = P.cpad / 32; tp.g.ntaps = L.ntaps;
+  tp.M = (int)M; tp.N = (int)p.F; tp.bn = L.bn; tp.tmem_cols = pow2_cols(L.bn);
+  return tc_launch(tp, L.ny, st);
+}
+
+size_t tc_dgrad_ws(const Plan& p, const std::vector<DgradClassPlan>& cls) {
+  TcPlanes P = tc_planes(0, p.N, p.F, p.Gp);
+  size_t off = P.end;
+  for (auto& c : cls) off = tc_layout(off, p.F, p.C, c.ntap).end;
+  return off;
+}
+
+int tc_dgrad(const Plan& p, const float* dy, const float* w, float* dx, void* ws, size_t ws_bytes,
+             cudaStream_t st) {
+  long long n_dx = p.N * p.C * p.Xp;
+  if (n_dx == 0) return 0;
+  std::vector<DgradClassPlan> cls;
+  size_t unused = 0;
+  dgrad_classes(p, sizeof(float), &cls, &unused);
+  size_t need = tc_dgrad_ws(p, cls);
+  if (ws_bytes < need || !ws) return fail("conv dgrad: workspace %zu < %zu bytes", ws_bytes, need);
+  if (dgrad_needs_memset(p, cls)) MGB_CUDA(cudaMemsetAsync(dx, 0, (size_t)n_dx * sizeof(float), st));
+  char* base = (char*)ws;
+  TcPlanes P = tc_planes(0, p.N, p.F, p.Gp);
+  float *ahi = (float*)(base + P.hi_off), *alo = (float*)(base + P.lo_off);
+  if (tc_prep_planes(dy, ahi, alo, p.N, p.F, p.Gp, P.cpad, st)) return 1;
+  size_t off = P.end;
+  for (auto& c : cls) {
+    TcLayout L = tc_layout(off, p.F, p.C, c.ntap);
+    off = L.end;
+    float *bhi = (float*)(base + L.bhi_off), *blo = (float*)(base + L.blo_off);
+    tc::TcTap* taps = (tc::TcTap*)(base + L.taps_off);
+    int* list = (int*)(base + L.list_off);
+    TapBuild tb;
+    for (int i = 0; i < 3; ++i) {
+      tb.cnt[i] = c.dev.cnt[i]; tb.W[i] = p.W[i]; tb.X[i] = p.G[i];
+      for (int k = 0; k < c.dev.cnt[i]; ++k) { tb.kidx[i][k] = c.dev.kidx[i][k]; tb.delta[i][k] = c.dev.e[i][k]; }
+    }
+    tb.cpad = P.cpad;
+    build_tc_taps<<<1, 256, 0, st>>>(taps, list, tb);
+    MGB_LAUNCH_CHECK();
+    tc::PackArgs pa{L.rows, L.cpad, (int)p.F, (int)p.C, (int)p.Wp, L.ntaps, 1};
+    tc::pack_filters_split<<<small_grid((long long)L.rows * L.K), 256, 0, st>>>(w, list, bhi, blo, pa);
+    MGB_LAUNCH_CHECK();
+    tc::TcParams tp;
+    tp.a_hi = ahi; tp.a_lo = alo; tp.taps = taps; tp.b_hi = bhi; tp.b_lo = blo; tp.out = dx;
+    tp.om.sample_stride = p.C * p.Xp; tp.om.chan_stride = p.Xp;
+    for (int i = 0; i < 3; ++i) {
+      tp.om.omul[i] = p.S[i]; tp.om.obase[i] = p.S[i] * c.qlo[i] + c.r[i] - p.Pd[i];
+      tp.g.P[i] = c.Q[i]; tp.g.pmul[i] = 1; tp.g.base[i] = c.qlo[i]; tp.g.X[i] = p.G[i];
+    }
+    tp.om.os[2] = 1; tp.om.os[1] = p.X[2]; tp.om.os[0] = p.X[1] * p.X[2];
+    tp.g.sample_stride = p.Gp * P.cpad; tp.g.pp = c.Q[0] * c.Q[1] * c.Q[2]; tp.g.cpad = P.cpad;
+    tp.g.nchunk = P.cpad / 32; tp.g.ntaps = L.ntaps;
+    tp.M = (int)(p.N * tp.g.pp); tp.N = (int)p.C; tp.bn = L.bn; tp.tmem_cols = pow2_cols(L.bn);
+    if (tc_launch(tp, L.ny, st)) return 1;
+  }
+  return 0;
+}
+
 // ---- the three convolutions ------------------------------------------------------------
 
 template <typename T>
@@ -421,10 +624,11 @@ extern "C" int mgb_conv_workspace_bytes(const mgb_conv_desc* d, int which, size_
   size_t esz = p.dtype == MGB_F32 ? 4 : 8;
   size_t need = 0;
   if (which == 0) {
-    need = (size_t)(p.C * p.Wp) * sizeof(TapEntry);
+    need = tc_eligible(p, 0) ? tc_fwd_ws(p) : (size_t)(p.C * p.Wp) * sizeof(TapEntry);
   } else if (which == 1) {
     std::vector<DgradClassPlan> cls;
     dgrad_classes(p, esz, &cls, &need);
+    if (tc_eligible(p, 1)) need = tc_dgrad_ws(p, cls);
   } else if (which == 2) {
     int s, k;
     if (p.F * p.C * p.Wp == 0 || p.N * p.Gp == 0) need = 0;
@@ -440,6 +644,8 @@ extern "C" int mgb_conv_fwd(const mgb_conv_desc* d, const void* x, const void* w
                             void* ws, size_t ws_bytes, void* stream) {
   Plan p;
   if (make_plan(d, &p)) return 1;
+  if (tc_eligible(p, 0))
+    return tc_fwd(p, (const float*)x, (const float*)w, (float*)y, ws, ws_bytes, as_stream(stream));
   if (p.dtype == MGB_F32)
     return fwd_t<float>(p, (const float*)x, (const float*)w, (float*)y, ws, ws_bytes, as_stream(stream));
   return fwd_t<double>(p, (const double*)x, (const double*)w, (double*)y, ws, ws_bytes, as_stream(stream));
@@ -449,6 +655,8 @@ extern "C" int mgb_conv_dgrad(const mgb_conv_desc* d, const void* dy, const void
                               void* ws, size_t ws_bytes, void* stream) {
   Plan p;
   if (make_plan(d, &p)) return 1;
+  if (tc_eligible(p, 1))
+    return tc_dgrad(p, (const float*)dy, (const float*)w, (float*)dx, ws, ws_bytes, as_stream(stream));
   if (p.dtype == MGB_F32)
     return dgrad_t<float>(p, (const float*)dy, (const float*)w, (float*)dx, ws, ws_bytes, as_stream(stream));
   return dgrad_t<double>(p, (const double*)dy, (const double*)w, (double*)dx, ws, ws_bytes, as_stream(stream));

@@ -1,0 +1,381 @@
+// FP32 convolution on the 5th-generation tensor cores: tcgen05.mma.kind::tf32 with the
+// accumulator in TMEM and a 3xTF32 split (a = a_hi + a_lo, both exactly TF32):
+//
+//     acc += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi          (fp32 accumulate in TMEM)
+//
+// Data flow of one conv GEMM  D[pixels, channels_out] = A[pixels, (tap, c)] * B[(tap, c), channels_out]:
+//
+//   1. a bandwidth-bound prep pass rewrites the gathered tensor (x for fwd, dy for dgrad)
+//      from NCX to channels-last [N][X...][Cpad] and splits it into hi / lo TF32 planes;
+//      the filter bank is packed to [rows][tap][Cpad] hi / lo the same way (tiny).
+//   2. the GEMM kernel is warp-specialised: 4 producer warps gather 128-byte channel
+//      vectors (one filter tap, 32 channels) per pixel row with 16-byte cp.async into the
+//      canonical K-major SWIZZLE_128B layout (zero-fill = padding), a single thread of
+//      warp 4 issues the tcgen05.mma stream, mbarriers pipeline the shared-memory ring,
+//      and the 4 producer warps turn into the epilogue: tcgen05.ld the TMEM accumulator
+//      and store it to the NCX output (lanes = consecutive pixels => coalesced).
+//
+// Descriptor encodings follow the PTX ISA "tcgen05 matrix/instruction descriptor" tables.
+#pragma once
+#include "conv_gemm.cuh"
+
+namespace mgb {
+namespace conv {
+namespace tc {
+
+constexpr int BM = 128;              // UMMA M: pixels per CTA tile (TMEM lanes)
+constexpr int BK = 32;               // tf32 per smem row = 128 bytes = one SWIZZLE_128B row
+constexpr int PRODUCERS = 128;       // 4 warps: producers, then epilogue
+constexpr int THREADS = PRODUCERS + 32;
+constexpr int A_TILE_BYTES = BM * 128;
+
+struct __align__(16) TcTap {
+  int off;             // ((d0*X1 + d1)*X2 + d2) * cpad   (elements of the channels-last source)
+  int d0, d1, d2;
+};
+
+struct TcGeom {
+  long long sample_stride;   // X0*X1*X2*cpad
+  int P[3];                  // pixel grid of the GEMM M dimension, per sample
+  int pmul[3], base[3];      // source coord = pixel*pmul + base (+ tap delta)
+  int X[3];                  // source spatial extents
+  int pp;                    // P0*P1*P2
+  int cpad;                  // channels per source pixel (multiple of 32)
+  int nchunk;                // cpad / 32
+  int ntaps;
+};
+
+struct TcParams {
+  const float* a_hi;
+  const float* a_lo;
+  const TcTap* taps;
+  const float* b_hi;         // [rows >= gridDim.y*bn][K], K = ntaps*cpad, K contiguous
+  const float* b_lo;
+  float* out;
+  OutMap om;
+  TcGeom g;
+  int M, N;                  // GEMM rows (pixels over the batch) and real output channels
+  int bn;                    // N tile: multiple of 16, 16..256
+  int tmem_cols;             // power of two >= max(32, bn)
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded spin: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar), done = 0;
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+}
+
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(slot)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, FP32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major operand, SWIZZLE_128B, rows of 128 bytes,
+// 8-row groups 1024 bytes apart (SBO); LBO is unused for swizzled K-major (set to 1)
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // [0,14)  start address >> 4
+  d |= (uint64_t)1 << 16;                          // [16,30) leading byte offset >> 4
+  d |= (uint64_t)(1024 >> 4) << 32;                // [32,46) stride byte offset >> 4
+  d |= (uint64_t)1 << 46;                          // [46,48) descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // [61,64) SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N=bn
+__host__ __device__ inline uint32_t idesc_tf32(int bn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+inline size_t smem_bytes(int bn, int stages) {
+  return (size_t)stages * (2 * A_TILE_BYTES + 2 * (size_t)bn * 128) + 1024 /*align*/ + 256 /*barriers*/;
+}
+
+// ---- the GEMM kernel -----------------------------------------------------------------------
+
+template <int STAGES>
+__global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = p.bn * 128;
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.bn;
+  const int S = p.g.ntaps * p.g.nchunk;          // K stages of 32 channels of one tap
+  const long long K = (long long)S * BK;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(full_bar + s, PRODUCERS);
+        mbar_init(empty_bar + s, 1);
+      }
+      mbar_init(accum_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===== producers: one A row (pixel) and bn/128 B rows per thread =====
+    const int r = tid;
+    int pix = m0 + r;
+    const bool pv = pix < p.M;
+    int n, q0, q1, q2;
+    {
+      int pp = pv ? pix : 0;
+      n = pp / p.g.pp;
+      int rem = pp - n * p.g.pp;
+      int q = rem / p.g.P[2];
+      q2 = rem - q * p.g.P[2];
+      q0 = q / p.g.P[1];
+      q1 = q - q0 * p.g.P[1];
+    }
+    const int c0 = q0 * p.g.pmul[0] + p.g.base[0];
+    const int c1 = q1 * p.g.pmul[1] + p.g.base[1];
+    const int c2 = q2 * p.g.pmul[2] + p.g.base[2];
+    const long long pix_off =
+        (long long)n * p.g.sample_stride +
+        (((long long)c0 * p.g.X[1] + c1) * p.g.X[2] + c2) * (long long)p.g.cpad;
+    const uint32_t swz = (uint32_t)(r & 7);
+    const uint32_t smem_base = smem_u32(smem);
+    const int b_rows = p.bn;   // rows r, r+128 (if bn > 128)
+
+    constexpr int LAG = STAGES - 1;   // cp.async groups in flight before the oldest is published
+    for (int s = 0; s < S; ++s) {
+      const int stage = s % STAGES;
+      if (s >= STAGES) mbar_wait(empty_bar + stage, (uint32_t)((s / STAGES - 1) & 1));
+      const int tap = s / p.g.nchunk, cc = s - tap * p.g.nchunk;
+      const int4 tv = __ldg(reinterpret_cast<const int4*>(p.taps) + tap);
+      const bool v = pv && (unsigned)(c0 + tv.y) < (unsigned)p.g.X[0] &&
+                     (unsigned)(c1 + tv.z) < (unsigned)p.g.X[1] &&
+                     (unsigned)(c2 + tv.w) < (unsigned)p.g.X[2];
+      const long long aoff = v ? (pix_off + tv.x + cc * BK) : 0;
+      const uint32_t a_hi_s = smem_base + stage * stage_bytes + r * 128;
+      const uint32_t a_lo_s = a_hi_s + A_TILE_BYTES;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t so = ((uint32_t)c ^ swz) << 4;
+        cp_async16(a_hi_s + so, p.a_hi + aoff + c * 4, v);
+        cp_async16(a_lo_s + so, p.a_lo + aoff + c * 4, v);
+      }
+      for (int br = r; br < b_rows; br += PRODUCERS) {
+        const long long boff = (long long)(n0 + br) * K + (long long)s * BK;
+        const uint32_t b_hi_s = smem_base + stage * stage_bytes + 2 * A_TILE_BYTES + br * 128;
+        const uint32_t b_lo_s = b_hi_s + b_tile_bytes;
+        const uint32_t bswz = (uint32_t)(br & 7);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t so = ((uint32_t)c ^ bswz) << 4;
+          cp_async16(b_hi_s + so, p.b_hi + boff + c * 4, true);
+          cp_async16(b_lo_s + so, p.b_lo + boff + c * 4, true);
+        }
+      }
+      cp_async_commit();
+      if (s >= LAG) {
+        cp_async_wait<LAG>();       // group of stage s-LAG has landed
+        fence_proxy_async();        // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(full_bar + (s - LAG) % STAGES);
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int s = (S > LAG ? S - LAG : 0); s < S; ++s) mbar_arrive(full_bar + s % STAGES);
+
+    // ===== epilogue: TMEM -> registers -> NCX output =====
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    long long rowoff = -1;
+    if (pv)
+      rowoff = (long long)n * p.om.sample_stride +
+               (long long)(q0 * p.om.omul[0] + p.om.obase[0]) * p.om.os[0] +
+               (long long)(q1 * p.om.omul[1] + p.om.obase[1]) * p.om.os[1] +
+               (long long)(q2 * p.om.omul[2] + p.om.obase[2]) * p.om.os[2];
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int col = 0; col < p.bn; col += 16) {
+      uint32_t v[16];
+      tmem_ld16(lane_base + (uint32_t)col, v);
+      if (rowoff >= 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int ch = n0 + col + j;
+          if (ch < p.N) p.out[rowoff + (long long)ch * p.om.chan_stride] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // ===== MMA issuer: one thread =====
+    const uint32_t idesc = idesc_tf32(p.bn);
+    const uint32_t smem_base = smem_u32(smem);
+    for (int s = 0; s < S; ++s) {
+      const int stage = s % STAGES;
+      mbar_wait(full_bar + stage, (uint32_t)((s / STAGES) & 1));
+      tc_fence_after();
+      const uint32_t a_hi = smem_base + stage * stage_bytes;
+      const uint32_t a_lo = a_hi + A_TILE_BYTES;
+      const uint32_t b_hi = a_lo + A_TILE_BYTES;
+      const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+      for (int j = 0; j < BK / 8; ++j) {   // 4 k-steps of 8 tf32 (32 bytes) inside the 128-byte row
+        const uint64_t dah = smem_desc_k_sw128(a_hi + j * 32), dal = smem_desc_k_sw128(a_lo + j * 32);
+        const uint64_t dbh = smem_desc_k_sw128(b_hi + j * 32), dbl = smem_desc_k_sw128(b_lo + j * 32);
+        umma_tf32(tmem_base, dal, dbh, idesc, (s | j) ? 1u : 0u);   // small cross terms first
+        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+        umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+      }
+      umma_commit(empty_bar + stage);      // frees the smem stage when these MMAs retire
+    }
+    umma_commit(accum_bar);                // accumulator complete
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---- prep kernels ----------------------------------------------------------------------------
+
+// x [N][C][P] (NCX) -> hi, lo [N][P][cpad] (channels last), TF32 split, zero channel padding
+__global__ void __launch_bounds__(256) nchw_to_nhwc_split(const float* __restrict__ x,
+                                                          float* __restrict__ hi,
+                                                          float* __restrict__ lo, int C, long long P,
+                                                          int cpad) {
+  __shared__ float tile[32][33];
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32, n = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c = c0 + ty + 8 * i;
+    long long pp = p0 + tx;
+    tile[ty + 8 * i][tx] = (c < C && pp < P) ? __ldg(x + ((long long)n * C + c) * P + pp) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long pp = p0 + ty + 8 * i;
+    int c = c0 + tx;
+    if (pp < P && c < cpad) {
+      float v = tile[tx][ty + 8 * i];
+      uint32_t h, l;
+      split_tf32(v, h, l);
+      long long o = ((long long)n * P + pp) * cpad + c;
+      hi[o] = __uint_as_float(h);
+      lo[o] = __uint_as_float(l);
+    }
+  }
+}
+
+// generic filter pack: out[row][tap_j][ch] = w[f][c][tap] with (row, ch) = (f, c) for fwd and
+// (c, f) for dgrad; rows/chs beyond the real extents are zero.  tap_list maps tap_j -> tap.
+struct PackArgs {
+  int rows, chs;          // padded extents of the packed matrix (rows, channels per tap)
+  int F, C, Wp;           // real filter bank extents
+  int ntaps;
+  int swap;               // 0: row = f, ch = c (fwd)   1: row = c, ch = f (dgrad)
+};
+
+__global__ void __launch_bounds__(256) pack_filters_split(const float* __restrict__ w,
+                                                          const int* __restrict__ tap_list,
+                                                          float* __restrict__ hi,
+                                                          float* __restrict__ lo, PackArgs a) {
+  long long total = (long long)a.rows * a.ntaps * a.chs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ch = (int)(i % a.chs);
+    long long t = i / a.chs;
+    int tj = (int)(t % a.ntaps);
+    int row = (int)(t / a.ntaps);
+    int f = a.swap ? ch : row, c = a.swap ? row : ch;
+    float v = 0.f;
+    if (f < a.F && c < a.C) v = __ldg(w + ((long long)f * a.C + c) * a.Wp + tap_list[tj]);
+    uint32_t h, l;
+    split_tf32(v, h, l);
+    hi[i] = __uint_as_float(h);
+    lo[i] = __uint_as_float(l);
+  }
+}
+
+}  // namespace tc
+}  // namespace conv
+}  // namespace mgb

@@ -197,6 +197,45 @@ def test_conv_tile_boundaries_vs_oracle(dtype):
         assert_close(wt.grad.get(), oc.conv_dw(g, x, w.shape, s, p, 1), dtype)
 
 
+TC_CASES = [
+    # N, C, F, X, W, stride, padding, dilation  (fp32, >= 16 channels in and out: tcgen05 path)
+    (2, 32, 32, (8, 8), (1, 1), 1, 0, 1),
+    (2, 32, 16, (9, 10), (3, 3), 1, 1, 1),
+    (3, 16, 48, (12, 11), (3, 2), 1, (1, 0), 1),
+    (2, 64, 128, (14, 14), (3, 3), 1, 1, 1),
+    (2, 40, 72, (13, 13), (3, 3), 2, 1, 1),
+    (2, 33, 130, (13, 13), (3, 3), 2, 0, 2),
+    (1, 96, 200, (7, 9), (2, 3), (1, 2), (0, 1), (2, 1)),
+    (3, 24, 20, (37,), (5,), 2, 2, 1),
+    (2, 32, 64, (6, 7, 8), (3, 3, 3), 1, 1, 1),
+    (2, 16, 16, (5, 9, 9), (2, 3, 3), (1, 2, 2), 0, 1),
+    (5, 32, 32, (30, 30), (3, 3), 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "x".join(map(str, c[:3])) + f"_{len(c[3])}d")
+@pytest.mark.parametrize("path", ["tc", "mma"])
+def test_conv_f32_paths_vs_oracle(case, path, monkeypatch):
+    """both fp32 kernels (tcgen05 3xTF32 and the mma.sync fallback) against the oracle"""
+    monkeypatch.setenv("MGB_CONV_F32_PATH", path)
+    N, C, F, X, W, s, p, d = case
+    rng = np.random.default_rng(hash(case) % (2 ** 32))
+    x = rng.standard_normal((N, C, *X)).astype(np.float32)
+    w = rng.standard_normal((F, C, *W)).astype(np.float32)
+    xt, wt = Tensor(x), Tensor(w)
+    y = conv_nd(xt, wt, stride=s, padding=p, dilation=d)
+    want = oc.conv_fwd(x.astype(np.float64), w.astype(np.float64), s, p, d)
+    assert y.shape == want.shape
+    assert_close(y.numpy(), want, np.float32, err_msg=f"{path} fwd {case}")
+    g = rng.standard_normal(want.shape).astype(np.float32)
+    y.backward(g)
+    g64 = g.astype(np.float64)
+    assert_close(xt.grad.get(), oc.conv_dx(g64, x.shape, w.astype(np.float64), s, p, d), np.float32,
+                 err_msg=f"{path} dx {case}")
+    assert_close(wt.grad.get(), oc.conv_dw(g64, x.astype(np.float64), w.shape, s, p, d), np.float32,
+                 err_msg=f"{path} dw {case}")
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_pool_random_vs_oracle_bit_exact(dtype):
     rng = np.random.default_rng(77)
