@@ -327,6 +327,11 @@ bool tc_eligible(const Plan& p, int which) {
   if (p.dtype != MGB_F32 || !tc_enabled()) return false;
   long long cin = which == 0 ? p.C : p.F, cout = which == 0 ? p.F : p.C;
   if (cin < 16 || cout < 16) return false;
+  if (which == 2) {
+    const char* e = getenv("MGB_WGRAD_F32_PATH");   // "mma" keeps wgrad on the mma.sync kernel
+    if (e && strcmp(e, "mma") == 0) return false;
+    if ((long long)round_up(p.F, 32) * p.Gp > INT32_MAX || p.N * p.Gp > INT32_MAX - 64) return false;
+  }
   if ((long long)round_up(cin, 32) * std::max(p.Xp, p.Gp) > INT32_MAX) return false;
   return true;
 }
@@ -511,6 +516,78 @@ int tc_dgrad(const Plan& p, const float* dy, const float* w, float* dx, void* ws
   return 0;
 }
 
+struct TcWgradLayout {
+  TcPlanes X, Y;            // channels-last planes of x and dy
+  int cblocks, nblocks, nt, nbpc, mt, splits, kps;
+  size_t taps_off, list_off, partial_off, end;
+};
+
+TcWgradLayout tc_wgrad_layout(const Plan& p) {
+  TcWgradLayout L;
+  L.X = tc_planes(0, p.N, p.C, p.Xp);
+  L.Y = tc_planes(L.X.end, p.N, p.F, p.Gp);
+  L.cblocks = L.X.cpad / 32;
+  L.nblocks = (int)p.Wp * L.cblocks;
+  L.nt = (L.nblocks + 7) / 8;
+  L.nbpc = (L.nblocks + L.nt - 1) / L.nt;
+  L.mt = (int)((p.F + tc::BM - 1) / tc::BM);
+  long long K = p.N * p.Gp;
+  int stages_total = (int)((K + tc::WG_KS - 1) / tc::WG_KS);
+  int want = std::max(1, sm_count() / (L.mt * L.nt));
+  int splits = std::max(1, std::min(want, std::max(1, stages_total / 32)));
+  int per = (stages_total + splits - 1) / splits;
+  L.splits = (stages_total + per - 1) / per;
+  L.kps = per * tc::WG_KS;
+  size_t off = align_up(L.Y.end, 256);
+  L.taps_off = off; off += align_up((size_t)p.Wp * sizeof(tc::TcTap), 256);
+  L.list_off = off; off += align_up((size_t)p.Wp * sizeof(int), 256);
+  L.partial_off = off; off += align_up((size_t)L.splits * p.F * p.C * p.Wp * sizeof(float), 256);
+  L.end = off;
+  return L;
+}
+
+int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes,
+             cudaStream_t st) {
+  long long n_dw = p.F * p.C * p.Wp;
+  if (n_dw == 0) return 0;
+  if (p.N * p.Gp == 0) { MGB_CUDA(cudaMemsetAsync(dw, 0, (size_t)n_dw * sizeof(float), st)); return 0; }
+  TcWgradLayout L = tc_wgrad_layout(p);
+  if (ws_bytes < L.end || !ws) return fail("conv wgrad: workspace %zu < %zu bytes", ws_bytes, L.end);
+  char* base = (char*)ws;
+  float *xhi = (float*)(base + L.X.hi_off), *xlo = (float*)(base + L.X.lo_off);
+  float *yhi = (float*)(base + L.Y.hi_off), *ylo = (float*)(base + L.Y.lo_off);
+  tc::TcTap* taps = (tc::TcTap*)(base + L.taps_off);
+  int* list = (int*)(base + L.list_off);
+  float* partial = (float*)(base + L.partial_off);
+  if (tc_prep_planes(x, xhi, xlo, p.N, p.C, p.Xp, L.X.cpad, st)) return 1;
+  if (tc_prep_planes(dy, yhi, ylo, p.N, p.F, p.Gp, L.Y.cpad, st)) return 1;
+  TapBuild tb;
+  for (int i = 0; i < 3; ++i) {
+    tb.cnt[i] = p.W[i]; tb.W[i] = p.W[i]; tb.X[i] = p.X[i];
+    for (int k = 0; k < p.W[i]; ++k) { tb.kidx[i][k] = (short)k; tb.delta[i][k] = (short)(k * p.D[i]); }
+  }
+  tb.cpad = L.X.cpad;
+  build_tc_taps<<<1, 256, 0, st>>>(taps, list, tb);
+  MGB_LAUNCH_CHECK();
+  tc::TcWgradParams wp;
+  wp.a_hi = yhi; wp.a_lo = ylo; wp.b_hi = xhi; wp.b_lo = xlo; wp.taps = taps; wp.partial = partial;
+  wp.fpad = L.Y.cpad; wp.cpad = L.X.cpad; wp.cblocks = L.cblocks;
+  wp.F = (int)p.F; wp.C = (int)p.C; wp.Wp = (int)p.Wp;
+  for (int i = 0; i < 3; ++i) { wp.G[i] = p.G[i]; wp.S[i] = p.S[i]; wp.Pd[i] = p.Pd[i]; wp.X[i] = p.X[i]; }
+  wp.gp = (int)p.Gp; wp.Ktot = (int)(p.N * p.Gp); wp.k_per_split = L.kps;
+  wp.nblocks_total = L.nblocks; wp.nbpc = L.nbpc; wp.tmem_cols = pow2_cols(L.nbpc * 32);
+  constexpr int STAGES = 4;
+  size_t smem = tc::wgrad_smem_bytes(L.nbpc, STAGES);
+  MGB_CUDA(cudaFuncSetAttribute(tc::wgrad_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  dim3 grid(L.mt, L.nt, L.splits);
+  tc::wgrad_tc_kernel<STAGES><<<grid, tc::THREADS, smem, st>>>(wp);
+  MGB_LAUNCH_CHECK();
+  splitk_reduce<float><<<small_grid(n_dw), 256, 0, st>>>(partial, dw, n_dw, L.splits);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- the three convolutions ------------------------------------------------------------
 
 template <typename T>
@@ -632,6 +709,7 @@ extern "C" int mgb_conv_workspace_bytes(const mgb_conv_desc* d, int which, size_
   } else if (which == 2) {
     int s, k;
     if (p.F * p.C * p.Wp == 0 || p.N * p.Gp == 0) need = 0;
+    else if (tc_eligible(p, 2)) need = tc_wgrad_layout(p).end;
     else need = p.dtype == MGB_F32 ? wgrad_ws<float>(p, &s, &k) : wgrad_ws<double>(p, &s, &k);
   } else {
     return fail("mgb_conv_workspace_bytes: which=%d", which);
@@ -666,6 +744,8 @@ extern "C" int mgb_conv_wgrad(const mgb_conv_desc* d, const void* dy, const void
                               void* ws, size_t ws_bytes, void* stream) {
   Plan p;
   if (make_plan(d, &p)) return 1;
+  if (tc_eligible(p, 2))
+    return tc_wgrad(p, (const float*)dy, (const float*)x, (float*)dw, ws, ws_bytes, as_stream(stream));
   if (p.dtype == MGB_F32)
     return wgrad_t<float>(p, (const float*)dy, (const float*)x, (float*)dw, ws, ws_bytes, as_stream(stream));
   return wgrad_t<double>(p, (const double*)dy, (const double*)x, (double*)dw, ws, ws_bytes, as_stream(stream));

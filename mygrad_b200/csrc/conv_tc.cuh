@@ -17,6 +17,8 @@
 //
 // Descriptor encodings follow the PTX ISA "tcgen05 matrix/instruction descriptor" tables.
 #pragma once
+#include <climits>
+
 #include "conv_gemm.cuh"
 
 namespace mgb {
@@ -197,29 +199,35 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // ===== producers: one A row (pixel) and bn/128 B rows per thread =====
-    const int r = tid;
-    int pix = m0 + r;
-    const bool pv = pix < p.M;
-    int n, q0, q1, q2;
-    {
+    // ===== producers =====
+    // Thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 16*i: one warp instruction then
+    // covers 4 whole 128-byte rows, so every L2 request is a full line (a lone 16-byte
+    // cp.async still moves a 32-byte sector).
+    const int chunk = tid & 7, rg = tid >> 3;
+    constexpr int ROWS = BM / 16;   // 8 A rows per thread
+    long long pix_off[ROWS];
+    int cc0[ROWS], cc1[ROWS], cc2[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+      int pix = m0 + rg + 16 * i;
+      bool pv = pix < p.M;
       int pp = pv ? pix : 0;
-      n = pp / p.g.pp;
+      int n = pp / p.g.pp;
       int rem = pp - n * p.g.pp;
       int q = rem / p.g.P[2];
-      q2 = rem - q * p.g.P[2];
-      q0 = q / p.g.P[1];
-      q1 = q - q0 * p.g.P[1];
+      int q2 = rem - q * p.g.P[2];
+      int q0 = q / p.g.P[1];
+      int q1 = q - q0 * p.g.P[1];
+      cc0[i] = pv ? q0 * p.g.pmul[0] + p.g.base[0] : INT_MIN / 2;   // invalid rows fail every bounds check
+      cc1[i] = q1 * p.g.pmul[1] + p.g.base[1];
+      cc2[i] = q2 * p.g.pmul[2] + p.g.base[2];
+      pix_off[i] = (long long)n * p.g.sample_stride +
+                   (((long long)(pv ? cc0[i] : 0) * p.g.X[1] + cc1[i]) * p.g.X[2] + cc2[i]) *
+                       (long long)p.g.cpad + chunk * 4;
     }
-    const int c0 = q0 * p.g.pmul[0] + p.g.base[0];
-    const int c1 = q1 * p.g.pmul[1] + p.g.base[1];
-    const int c2 = q2 * p.g.pmul[2] + p.g.base[2];
-    const long long pix_off =
-        (long long)n * p.g.sample_stride +
-        (((long long)c0 * p.g.X[1] + c1) * p.g.X[2] + c2) * (long long)p.g.cpad;
-    const uint32_t swz = (uint32_t)(r & 7);
+    const uint32_t so = (uint32_t)(chunk ^ (rg & 7)) << 4;   // (rg + 16 i) & 7 == rg & 7
     const uint32_t smem_base = smem_u32(smem);
-    const int b_rows = p.bn;   // rows r, r+128 (if bn > 128)
+    const int b_iters = p.bn / 16;
 
     constexpr int LAG = STAGES - 1;   // cp.async groups in flight before the oldest is published
     for (int s = 0; s < S; ++s) {
@@ -227,29 +235,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
       if (s >= STAGES) mbar_wait(empty_bar + stage, (uint32_t)((s / STAGES - 1) & 1));
       const int tap = s / p.g.nchunk, cc = s - tap * p.g.nchunk;
       const int4 tv = __ldg(reinterpret_cast<const int4*>(p.taps) + tap);
-      const bool v = pv && (unsigned)(c0 + tv.y) < (unsigned)p.g.X[0] &&
-                     (unsigned)(c1 + tv.z) < (unsigned)p.g.X[1] &&
-                     (unsigned)(c2 + tv.w) < (unsigned)p.g.X[2];
-      const long long aoff = v ? (pix_off + tv.x + cc * BK) : 0;
-      const uint32_t a_hi_s = smem_base + stage * stage_bytes + r * 128;
+      const long long toff = (long long)tv.x + cc * BK;
+      const uint32_t a_hi_s = smem_base + stage * stage_bytes + rg * 128 + so;
       const uint32_t a_lo_s = a_hi_s + A_TILE_BYTES;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t so = ((uint32_t)c ^ swz) << 4;
-        cp_async16(a_hi_s + so, p.a_hi + aoff + c * 4, v);
-        cp_async16(a_lo_s + so, p.a_lo + aoff + c * 4, v);
+      for (int i = 0; i < ROWS; ++i) {
+        const bool v = (unsigned)(cc0[i] + tv.y) < (unsigned)p.g.X[0] &&
+                       (unsigned)(cc1[i] + tv.z) < (unsigned)p.g.X[1] &&
+                       (unsigned)(cc2[i] + tv.w) < (unsigned)p.g.X[2];
+        const long long aoff = v ? (pix_off[i] + toff) : 0;
+        cp_async16(a_hi_s + i * 2048, p.a_hi + aoff, v);
+        cp_async16(a_lo_s + i * 2048, p.a_lo + aoff, v);
       }
-      for (int br = r; br < b_rows; br += PRODUCERS) {
-        const long long boff = (long long)(n0 + br) * K + (long long)s * BK;
-        const uint32_t b_hi_s = smem_base + stage * stage_bytes + 2 * A_TILE_BYTES + br * 128;
-        const uint32_t b_lo_s = b_hi_s + b_tile_bytes;
-        const uint32_t bswz = (uint32_t)(br & 7);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t so = ((uint32_t)c ^ bswz) << 4;
-          cp_async16(b_hi_s + so, p.b_hi + boff + c * 4, true);
-          cp_async16(b_lo_s + so, p.b_lo + boff + c * 4, true);
-        }
+      const uint32_t b_hi_s = smem_base + stage * stage_bytes + 2 * A_TILE_BYTES + rg * 128 + so;
+      const uint32_t b_lo_s = b_hi_s + b_tile_bytes;
+      const long long boff0 = (long long)(n0 + rg) * K + (long long)s * BK + chunk * 4;
+      for (int i = 0; i < b_iters; ++i) {
+        const long long boff = boff0 + (long long)(16 * i) * K;
+        cp_async16(b_hi_s + i * 2048, p.b_hi + boff, true);
+        cp_async16(b_lo_s + i * 2048, p.b_lo + boff, true);
       }
       cp_async_commit();
       if (s >= LAG) {
@@ -261,6 +265,21 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     cp_async_wait<0>();
     fence_proxy_async();
     for (int s = (S > LAG ? S - LAG : 0); s < S; ++s) mbar_arrive(full_bar + s % STAGES);
+
+    // epilogue row of this thread: TMEM lane == tile row == tid
+    const int r = tid;
+    const int pix = m0 + r;
+    const bool pv = pix < p.M;
+    int n, q0, q1, q2;
+    {
+      int pp = pv ? pix : 0;
+      n = pp / p.g.pp;
+      int rem = pp - n * p.g.pp;
+      int q = rem / p.g.P[2];
+      q2 = rem - q * p.g.P[2];
+      q0 = q / p.g.P[1];
+      q1 = q - q0 * p.g.P[1];
+    }
 
     // ===== epilogue: TMEM -> registers -> NCX output =====
     mbar_wait(accum_bar, 0);
@@ -306,6 +325,225 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
       umma_commit(empty_bar + stage);      // frees the smem stage when these MMAs retire
     }
     umma_commit(accum_bar);                // accumulator complete
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---- wgrad on the tensor cores --------------------------------------------------------------
+//
+//   dw[f, c, tap] = sum_pix dy[pix, f] * x[pix (+) tap, c]
+//
+// GEMM with M = f (128 per CTA), N = (tap, c) blocks of 32 channels, K = output pixels,
+// split-K over pixels.  Both operands come from the channels-last planes, so for a fixed
+// pixel (= k) the 32 channels of a block are one contiguous 128-byte row: the canonical
+// MN-major layout.  For 32-bit (TF32) MN-major operands the only legal shared-memory layout
+// is SWIZZLE_128B_BASE32B: atoms of 4 k-rows x 128 B, 32-byte chunks XOR-swizzled with the
+// row index (Swizzle<2,5,2> on the byte address).  A stage is [k-atom][block][4 k-rows][128 B].
+
+constexpr int WG_KS = 16;               // pixels per pipeline stage (two UMMA K=8 groups)
+constexpr int WG_A_PLANE = WG_KS * 512; // 128 f-channels * 4 B per pixel
+
+struct TcWgradParams {
+  const float* a_hi;     // dy planes [N*Gp][fpad]
+  const float* a_lo;
+  const float* b_hi;     // x planes  [N*Xp][cpad]
+  const float* b_lo;
+  const TcTap* taps;     // every filter tap: off = ((d0*X1+d1)*X2+d2)*cpad, d = k*dil
+  float* partial;        // [splits][F][C][Wp]
+  int fpad, cpad, cblocks;
+  int F, C, Wp;
+  int G[3], S[3], Pd[3], X[3];
+  int gp;                // G0*G1*G2
+  int Ktot;              // N * gp
+  int k_per_split;       // multiple of WG_KS
+  int nblocks_total;     // Wp * cblocks
+  int nbpc;              // (tap, c-block) blocks per CTA, <= 8
+  int tmem_cols;
+};
+
+// MN-major SWIZZLE_128B_BASE32B descriptor: LBO = byte distance between 32-element MN
+// blocks, SBO = byte distance between atoms of 4 k-rows
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;          // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+// byte offset of 16-byte chunk c (0..7) inside k-row `row` of a BASE32B atom
+__device__ __forceinline__ uint32_t base32b_chunk(uint32_t c, uint32_t row) {
+  return ((((c >> 1) ^ (row & 3u)) << 5) | ((c & 1u) << 4));
+}
+
+inline size_t wgrad_smem_bytes(int nbpc, int stages) {
+  return (size_t)stages * (2 * WG_A_PLANE + 2 * (size_t)WG_KS * nbpc * 128) + 1024 + 256;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ TcWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int bn = p.nbpc * 32;
+  const int b_plane = WG_KS * p.nbpc * 128;          // bytes of one B plane per stage
+  const int b_atom = p.nbpc * 512;                   // bytes of one k-atom (4 pixels) of B
+  const int b_group = 2 * b_atom;                    // bytes of one UMMA K=8 slice of B
+  const int stage_bytes = 2 * WG_A_PLANE + 2 * b_plane;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM;
+  const int blk0 = blockIdx.y * p.nbpc;              // first (tap, c-block) block of this CTA
+  const int kbeg = blockIdx.z * p.k_per_split;
+  const int kend = min(p.Ktot, kbeg + p.k_per_split);
+  const int S = (kend - kbeg + WG_KS - 1) / WG_KS;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(full_bar + s, PRODUCERS);
+        mbar_init(empty_bar + s, 1);
+      }
+      mbar_init(accum_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    const uint32_t smem_base = smem_u32(smem);
+    // A (dy): chunk32 = 16-byte chunk of the 512-byte f-vector, 4 pixels per pass
+    const int a_chunk = tid & 31, a_p0 = tid >> 5;
+    const bool a_fvalid = (m0 + a_chunk * 4) < p.fpad;
+    const uint32_t a_blk = (uint32_t)(a_chunk >> 3) * 512, a_c = (uint32_t)(a_chunk & 7);
+    // B (x): one pixel per thread and stage, chunk c of every block
+    const int b_c = tid & 7, b_p = tid >> 3;                 // b_p in [0,16)
+    const uint32_t b_dst0 = (uint32_t)(b_p >> 2) * b_atom + (uint32_t)(b_p & 3) * 128 +
+                            base32b_chunk((uint32_t)b_c, (uint32_t)b_p);
+
+    constexpr int LAG = STAGES - 1;
+    for (int s = 0; s < S; ++s) {
+      const int stage = s % STAGES;
+      if (s >= STAGES) mbar_wait(empty_bar + stage, (uint32_t)((s / STAGES - 1) & 1));
+      const int k0 = kbeg + s * WG_KS;
+      const uint32_t st_base = smem_base + stage * stage_bytes;
+      // ---- A planes
+#pragma unroll
+      for (int i = 0; i < WG_KS / 4; ++i) {
+        const int pl = a_p0 + 4 * i;                          // pixel within the stage
+        const int kp = k0 + pl;
+        const bool v = a_fvalid && kp < kend;
+        const long long off = v ? ((long long)kp * p.fpad + m0 + a_chunk * 4) : 0;
+        const uint32_t dst = st_base + (uint32_t)(pl >> 2) * 2048 + a_blk + (uint32_t)(pl & 3) * 128 +
+                             base32b_chunk(a_c, (uint32_t)pl);
+        cp_async16(dst, p.a_hi + off, v);
+        cp_async16(dst + WG_A_PLANE, p.a_lo + off, v);
+      }
+      // ---- B planes: decode this thread's pixel, then one row per (tap, c-block) block
+      {
+        const int kp = k0 + b_p;
+        const bool pv = kp < kend;
+        const int kk = pv ? kp : 0;
+        const int n = kk / p.gp;
+        int rem = kk - n * p.gp;
+        const int q = rem / p.G[2];
+        const int g2 = rem - q * p.G[2];
+        const int g0 = q / p.G[1];
+        const int g1 = q - g0 * p.G[1];
+        const int c0 = g0 * p.S[0] - p.Pd[0], c1 = g1 * p.S[1] - p.Pd[1], c2 = g2 * p.S[2] - p.Pd[2];
+        const long long xoff =
+            ((((long long)n * p.X[0] + c0) * p.X[1] + c1) * p.X[2] + c2) * (long long)p.cpad + b_c * 4;
+        const uint32_t dst0 = st_base + 2 * WG_A_PLANE + b_dst0;
+        for (int b = 0; b < p.nbpc; ++b) {
+          const int gb = blk0 + b;
+          const int tap = gb / p.cblocks, cb = gb - tap * p.cblocks;
+          bool v = pv && gb < p.nblocks_total;
+          int4 tv = make_int4(0, 0, 0, 0);
+          if (v) tv = __ldg(reinterpret_cast<const int4*>(p.taps) + tap);
+          v = v && (unsigned)(c0 + tv.y) < (unsigned)p.X[0] && (unsigned)(c1 + tv.z) < (unsigned)p.X[1] &&
+              (unsigned)(c2 + tv.w) < (unsigned)p.X[2];
+          const long long off = v ? (xoff + tv.x + cb * 32) : 0;
+          const uint32_t dst = dst0 + (uint32_t)b * 512;
+          cp_async16(dst, p.b_hi + off, v);
+          cp_async16(dst + b_plane, p.b_lo + off, v);
+        }
+      }
+      cp_async_commit();
+      if (s >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        mbar_arrive(full_bar + (s - LAG) % STAGES);
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int s = (S > LAG ? S - LAG : 0); s < S; ++s) mbar_arrive(full_bar + s % STAGES);
+
+    // ===== epilogue: lane = f, columns = (block, channel-in-block) -> partial[f][c][tap] =====
+    float* out = p.partial + (long long)blockIdx.z * p.F * p.C * p.Wp;
+    const int f = m0 + tid;
+    if (S > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int col = 0; col < bn; col += 16) {
+      uint32_t v[16];
+      if (S > 0) {
+        tmem_ld16(lane_base + (uint32_t)col, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      const int gb = blk0 + (col >> 5);
+      const int tap = gb / p.cblocks, cb = gb - tap * p.cblocks;
+      if (f < p.F && gb < p.nblocks_total) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int c = cb * 32 + (col & 31) + j;
+          if (c < p.C) out[((long long)f * p.C + c) * p.Wp + tap] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = idesc_tf32(bn) | (1u << 15) | (1u << 16);   // A and B MN-major
+    const uint32_t smem_base = smem_u32(smem);
+    for (int s = 0; s < S; ++s) {
+      const int stage = s % STAGES;
+      mbar_wait(full_bar + stage, (uint32_t)((s / STAGES) & 1));
+      tc_fence_after();
+      const uint32_t a_hi = smem_base + stage * stage_bytes;
+      const uint32_t a_lo = a_hi + WG_A_PLANE;
+      const uint32_t b_hi = a_lo + WG_A_PLANE;
+      const uint32_t b_lo = b_hi + b_plane;
+#pragma unroll
+      for (int j = 0; j < WG_KS / 8; ++j) {
+        // LBO = 512 B between 32-channel blocks, SBO = distance between 4-pixel k-atoms
+        const uint64_t dah = smem_desc_mn_sw128(a_hi + j * 4096, 512u, 2048u);
+        const uint64_t dal = smem_desc_mn_sw128(a_lo + j * 4096, 512u, 2048u);
+        const uint64_t dbh = smem_desc_mn_sw128(b_hi + j * b_group, 512u, (uint32_t)b_atom);
+        const uint64_t dbl = smem_desc_mn_sw128(b_lo + j * b_group, 512u, (uint32_t)b_atom);
+        umma_tf32(tmem_base, dal, dbh, idesc, (s | j) ? 1u : 0u);
+        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+        umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+      }
+      umma_commit(empty_bar + stage);
+    }
+    if (S > 0) umma_commit(accum_bar);
   }
 
   tc_fence_before();

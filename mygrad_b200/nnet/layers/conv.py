@@ -23,6 +23,22 @@ __all__ = ["conv_nd", "ConvND"]
 
 _MAX_SPATIAL = 3
 
+# One grow-only scratch buffer per stream, shared by every conv call on that stream: the
+# kernels of consecutive calls are ordered on the stream, so the buffer can be re-used as
+# soon as the next call is enqueued.  (Allocating multi-GB scratch per call makes the
+# stream-ordered pool grow and trim, which costs tens of milliseconds when it happens.)
+_WORKSPACES: dict = {}
+
+
+def _scratch(nbytes: int) -> DeviceArray:
+    key = current_stream()
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.nbytes < nbytes:
+        _WORKSPACES[key] = None  # drop the old buffer before asking for a bigger one
+        buf = DeviceArray(((nbytes * 5 // 4 + 7) // 8,), np.float64)
+        _WORKSPACES[key] = buf
+    return buf
+
 
 def _as_tuple(value, n: int, *, minimum: int, name: str) -> Tuple[int, ...]:
     """int -> n-tuple; sequences must have length n and integer entries >= minimum.
@@ -106,7 +122,7 @@ class ConvND(Operation):
         check(lib.mgb_conv_workspace_bytes(C.byref(self._desc), which, C.byref(n)))
         if n.value == 0:
             return None, 0
-        return DeviceArray((n.value + 7) // 8, np.float64), n.value
+        return _scratch(n.value), n.value
 
     def backward_var(self, grad: DeviceArray, index: int, **kwargs) -> DeviceArray:
         x, w = (v.data for v in self.variables)
