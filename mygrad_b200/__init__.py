@@ -19,6 +19,7 @@ from .device_array import (
     current_stream,
     device_available,
     empty,
+    empty_cache,
     full,
     full_like,
     pinned_empty,
@@ -39,7 +40,7 @@ __version__ = "0.1.0"
 __all__ = [
     "Tensor", "tensor", "asarray", "Operation", "execute_op", "no_autodiff",
     "DeviceArray", "asdevice", "empty", "zeros", "full", "full_like", "pinned_empty",
-    "current_stream", "set_stream", "synchronize", "device_available",
+    "current_stream", "set_stream", "synchronize", "device_available", "empty_cache",
     "InvalidGradient", "InvalidBackprop", "DisconnectedView", "SkipGradient",
     "nnet", "conv_nd", "max_pool", "mean_pool", "lib", "LIB_PATH",
 ]

@@ -174,15 +174,18 @@ struct Cfg {
 
 // One BK-deep slab of MMAs for a warp.  A_MMAJOR: A stage is [k][m] (fwd-like),
 // otherwise [m][k] (wgrad).  B stage is always [n][k].
-template <typename T, typename C, bool A_MMAJOR>
+// `hook(kk)` runs before k-step kk: the caller uses it to issue one slice of the next tile's
+// cp.async traffic, so that address arithmetic fills the issue slots between tensor ops.
+template <typename T, typename C, bool A_MMAJOR, typename Hook>
 __device__ __forceinline__ void mma_slab(const T* __restrict__ As, const T* __restrict__ Bs,
                                          float (&accf)[C::MI][C::NI][4],
                                          double (&accd)[C::MI][C::NI][2], int warp_m, int warp_n,
-                                         int lane) {
+                                         int lane, Hook hook) {
   const int lr = lane >> 2, lk = lane & 3;
   if constexpr (C::F64) {
 #pragma unroll
     for (int kk = 0; kk < C::BK / 4; ++kk) {
+      hook(kk);
       double a[C::MI], b[C::NI];
       const int k = kk * 4 + lk;
 #pragma unroll
@@ -200,6 +203,7 @@ __device__ __forceinline__ void mma_slab(const T* __restrict__ As, const T* __re
   } else {
 #pragma unroll
     for (int kk = 0; kk < C::BK / 8; ++kk) {
+      hook(kk);
       uint32_t ahi[C::MI][4], alo[C::MI][4], bhi[C::NI][2], blo[C::NI][2];
       const int k0 = kk * 8 + lk, k1 = k0 + 4;
 #pragma unroll
@@ -292,12 +296,16 @@ conv_fwdlike_kernel(const __grid_constant__ FwdParams<T> p) {
 
   const int KT = (p.K + C::BK - 1) / C::BK;
 
-  auto load_tile = [&](int stage, int kt) {
+  constexpr int PARTS = C::BK / C::FK;            // one slice per MMA k-step
+  constexpr int A_ELEMS = C::BK / AKSTEP, B_ELEMS = C::BN / BNSTEP;
+  // slice `part` of PARTS of the tile's copies (part < 0: everything)
+  auto load_tile = [&](int stage, int kt, int part) {
     const int k0 = kt * C::BK;
     T* as = As + stage * C::A_STAGE_M;
     T* bs = Bs + stage * C::B_STAGE;
 #pragma unroll
-    for (int j = 0; j < C::BK / AKSTEP; ++j) {
+    for (int j = 0; j < A_ELEMS; ++j) {
+      if (part >= 0 && (j * PARTS) / A_ELEMS != part) continue;
       int kc = akc0 + j * AKSTEP, k = k0 + kc;
       bool v = k < p.K;
       TapEntry te = load_tap(p.tab, v ? k : 0);
@@ -307,7 +315,8 @@ conv_fwdlike_kernel(const __grid_constant__ FwdParams<T> p) {
     }
     const bool kv = (k0 + bkc) < p.K;
 #pragma unroll
-    for (int j = 0; j < C::BN / BNSTEP; ++j) {
+    for (int j = 0; j < B_ELEMS; ++j) {
+      if (part >= 0 && (j * PARTS) / B_ELEMS != part) continue;
       int n = bn0 + j * BNSTEP;
       bool v = kv && (n0 + n) < p.N;
       const T* g = v ? (p.B + (long long)(n0 + n) * p.ldb + k0 + bkc) : p.B;
@@ -327,18 +336,20 @@ conv_fwdlike_kernel(const __grid_constant__ FwdParams<T> p) {
 
 #pragma unroll
   for (int s = 0; s < C::STAGES - 1; ++s) {
-    if (s < KT) load_tile(s, s);
+    if (s < KT) load_tile(s, s, -1);
     cp_async_commit();
   }
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<C::STAGES - 2>();
     __syncthreads();
-    int nk = kt + C::STAGES - 1;
-    if (nk < KT) load_tile(nk % C::STAGES, nk);
-    cp_async_commit();
-    int stage = kt % C::STAGES;
+    const int nk = kt + C::STAGES - 1;
+    const bool more = nk < KT;
+    const int stage = kt % C::STAGES;
     mma_slab<T, C, true>(As + stage * C::A_STAGE_M, Bs + stage * C::B_STAGE, accf, accd, warp_m,
-                         warp_n, lane);
+                         warp_n, lane, [&](int part) {
+                           if (more) load_tile(nk % C::STAGES, nk, part);
+                         });
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
@@ -439,7 +450,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams<T> p) {
     cp_async_commit();
     int stage = kt % C::STAGES;
     mma_slab<T, C, false>(As + stage * C::A_STAGE_K, Bs + stage * C::B_STAGE, accf, accd, warp_m,
-                          warp_n, lane);
+                          warp_n, lane, [](int) {});
   }
   cp_async_wait<0>();
 

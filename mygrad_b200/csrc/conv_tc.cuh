@@ -94,6 +94,12 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool p
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
 }
 
+// arrive on `bar` (without bumping its pending count) once all cp.async issued so far by
+// this thread have landed: the copy engine publishes the stage, the thread never blocks
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
@@ -229,7 +235,6 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     const uint32_t smem_base = smem_u32(smem);
     const int b_iters = p.bn / 16;
 
-    constexpr int LAG = STAGES - 1;   // cp.async groups in flight before the oldest is published
     for (int s = 0; s < S; ++s) {
       const int stage = s % STAGES;
       if (s >= STAGES) mbar_wait(empty_bar + stage, (uint32_t)((s / STAGES - 1) & 1));
@@ -255,16 +260,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         cp_async16(b_hi_s + i * 2048, p.b_hi + boff, true);
         cp_async16(b_lo_s + i * 2048, p.b_lo + boff, true);
       }
-      cp_async_commit();
-      if (s >= LAG) {
-        cp_async_wait<LAG>();       // group of stage s-LAG has landed
-        fence_proxy_async();        // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(full_bar + (s - LAG) % STAGES);
-      }
+      // publish asynchronously: the barrier completes when all 128 producers' copies landed.
+      // (The consumer issues the generic->async proxy fence after its wait.)
+      cp_async_arrive_noinc(full_bar + stage);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int s = (S > LAG ? S - LAG : 0); s < S; ++s) mbar_arrive(full_bar + s % STAGES);
 
     // epilogue row of this thread: TMEM lane == tile row == tid
     const int r = tid;
@@ -309,6 +308,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     for (int s = 0; s < S; ++s) {
       const int stage = s % STAGES;
       mbar_wait(full_bar + stage, (uint32_t)((s / STAGES) & 1));
+      fence_proxy_async();     // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
       tc_fence_after();
       const uint32_t a_hi = smem_base + stage * stage_bytes;
       const uint32_t a_lo = a_hi + A_TILE_BYTES;
@@ -434,7 +434,6 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     const uint32_t b_dst0 = (uint32_t)(b_p >> 2) * b_atom + (uint32_t)(b_p & 3) * 128 +
                             base32b_chunk((uint32_t)b_c, (uint32_t)b_p);
 
-    constexpr int LAG = STAGES - 1;
     for (int s = 0; s < S; ++s) {
       const int stage = s % STAGES;
       if (s >= STAGES) mbar_wait(empty_bar + stage, (uint32_t)((s / STAGES - 1) & 1));
@@ -481,16 +480,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
           cp_async16(dst + b_plane, p.b_lo + off, v);
         }
       }
-      cp_async_commit();
-      if (s >= LAG) {
-        cp_async_wait<LAG>();
-        fence_proxy_async();
-        mbar_arrive(full_bar + (s - LAG) % STAGES);
-      }
+      cp_async_arrive_noinc(full_bar + stage);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int s = (S > LAG ? S - LAG : 0); s < S; ++s) mbar_arrive(full_bar + s % STAGES);
 
     // ===== epilogue: lane = f, columns = (block, channel-in-block) -> partial[f][c][tap] =====
     float* out = p.partial + (long long)blockIdx.z * p.F * p.C * p.Wp;
@@ -525,6 +516,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     for (int s = 0; s < S; ++s) {
       const int stage = s % STAGES;
       mbar_wait(full_bar + stage, (uint32_t)((s / STAGES) & 1));
+      fence_proxy_async();     // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
       tc_fence_after();
       const uint32_t a_hi = smem_base + stage * stage_bytes;
       const uint32_t a_lo = a_hi + WG_A_PLANE;

@@ -27,6 +27,7 @@ __all__ = [
     "set_stream",
     "synchronize",
     "device_available",
+    "empty_cache",
 ]
 
 _SUPPORTED = (np.dtype(np.float32), np.dtype(np.float64))
@@ -61,22 +62,55 @@ def dtype_code(dtype) -> int:
     raise TypeError(f"mygrad_b200 supports float32 and float64 device arrays, got {dt}")
 
 
-class _Allocation:
-    """owns one device allocation; freed (stream-ordered) when the last view dies"""
+# Exact-size block cache in front of the stream-ordered pool.  A training loop asks for
+# the same sizes every step; handing a freed block straight to the next request of that
+# size costs no driver call and never makes the pool grow or trim (which shows up as
+# multi-millisecond hiccups with GB-sized activations).  Re-use is safe in stream order:
+# every kernel of the previous owner was enqueued on the stream before the new owner's.
+_CACHE: dict = {}          # (stream, nbytes) -> [ptr, ...]
+_CACHE_LIMIT = int(64e9)   # bytes kept at most; beyond it blocks go back to the pool
+_cached_bytes = 0
 
-    __slots__ = ("ptr", "nbytes")
+
+def empty_cache() -> None:
+    """returns every cached block to the driver's stream-ordered pool"""
+    global _cached_bytes
+    for (stream, _), ptrs in list(_CACHE.items()):
+        for p in ptrs:
+            lib.mgb_free_async(C.c_void_p(p), C.c_void_p(stream))
+    _CACHE.clear()
+    _cached_bytes = 0
+
+
+class _Allocation:
+    """owns one device allocation; recycled (stream-ordered) when the last view dies"""
+
+    __slots__ = ("ptr", "nbytes", "stream")
 
     def __init__(self, nbytes: int):
+        self.nbytes = max(16, (nbytes + 511) // 512 * 512)
+        self.stream = _stream
+        free = _CACHE.get((self.stream, self.nbytes))
+        if free:
+            global _cached_bytes
+            self.ptr = free.pop()
+            _cached_bytes -= self.nbytes
+            return
         p = C.c_void_p()
-        check(lib.mgb_malloc_async(C.byref(p), C.c_size_t(nbytes), C.c_void_p(_stream)))
+        check(lib.mgb_malloc_async(C.byref(p), C.c_size_t(self.nbytes), C.c_void_p(_stream)))
         self.ptr = int(p.value or 0)
-        self.nbytes = nbytes
 
     def __del__(self):
         try:
-            if self.ptr:
-                lib.mgb_free_async(C.c_void_p(self.ptr), C.c_void_p(_stream))
-                self.ptr = 0
+            global _cached_bytes
+            if not self.ptr:
+                return
+            if _cached_bytes + self.nbytes <= _CACHE_LIMIT:
+                _CACHE.setdefault((self.stream, self.nbytes), []).append(self.ptr)
+                _cached_bytes += self.nbytes
+            else:
+                lib.mgb_free_async(C.c_void_p(self.ptr), C.c_void_p(self.stream))
+            self.ptr = 0
         except Exception:  # interpreter shutdown
             pass
 
