@@ -98,6 +98,51 @@ __global__ void __launch_bounds__(256) pool_max_fwd_pair(PoolGeom g, const T* __
   }
 }
 
+// Same case (last axis pooled in pairs) with VW outputs per thread: every window row is
+// 2*VW contiguous elements = two 16-byte loads, all issued before any compare, so a
+// thread keeps 32*P0*P1 bytes in flight (HBM latency needs the memory-level parallelism).
+template <typename T, int VW>
+__global__ void __launch_bounds__(256) pool_max_fwd_vec(PoolGeom g, const T* __restrict__ x,
+                                                        T* __restrict__ y, long long total_vec) {
+  constexpr int EPV = 16 / sizeof(T);          // elements per 16-byte vector
+  constexpr int NV = 2 * VW / EPV;             // vectors per window row (== 2)
+  const int gv = g.G[2] / VW;                  // vector groups per output row
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total_vec;
+       o += (long long)gridDim.x * blockDim.x) {
+    long long t = o;
+    int v2 = (int)(t % gv); t /= gv;
+    int g1 = (int)(t % g.G[1]); t /= g.G[1];
+    int g0 = (int)(t % g.G[0]);
+    long long l = t / g.G[0];
+    const T* base = x + l * g.x_per_lead +
+                    ((long long)(g0 * g.S[0]) * g.X[1] + g1 * g.S[1]) * g.X[2] + v2 * (2 * VW);
+    T best[VW];
+    bool first = true;
+    for (int p0 = 0; p0 < g.P[0]; ++p0)
+      for (int p1 = 0; p1 < g.P[1]; ++p1) {
+        float4 raw[NV];
+        const float4* row = reinterpret_cast<const float4*>(base + ((long long)p0 * g.X[1] + p1) * g.X[2]);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) raw[k] = __ldg(row + k);
+        const T* e = reinterpret_cast<const T*>(raw);
+#pragma unroll
+        for (int w = 0; w < VW; ++w) {
+          T a = e[2 * w], b = e[2 * w + 1];
+          if (first) best[w] = a; else if (beats(a, best[w])) best[w] = a;
+          if (beats(b, best[w])) best[w] = b;
+        }
+        first = false;
+      }
+    float4 out;
+    T* oe = reinterpret_cast<T*>(&out);
+#pragma unroll
+    for (int w = 0; w < VW; ++w) oe[w] = best[w];
+    T* dst = y + l * g.g_per_lead + ((long long)g0 * g.G[1] + g1) * g.G[2] + v2 * VW;
+    if (VW * sizeof(T) == 16) *reinterpret_cast<float4*>(dst) = out;
+    else *reinterpret_cast<float2*>(dst) = *reinterpret_cast<float2*>(&out);
+  }
+}
+
 // ---- backward --------------------------------------------------------------
 
 // window-centric, for exact non-overlapping tilings (S == P on every axis) whose
@@ -138,6 +183,70 @@ __global__ void __launch_bounds__(256) pool_max_bwd_tile_pair(PoolGeom g, const 
         out.y = (arg == idx + 1) ? gval : (T)0;
         *reinterpret_cast<V*>(dx + off + ((long long)p0 * g.X[1] + p1) * g.X[2]) = out;
         idx += 2;
+      }
+  }
+}
+
+// window-centric, exact tiling, last axis in pairs, VW windows per thread (see pool_max_fwd_vec)
+template <typename T, int VW, int MAXROWS>
+__global__ void __launch_bounds__(256) pool_max_bwd_tile_vec(PoolGeom g, const T* __restrict__ dy,
+                                                             const T* __restrict__ x,
+                                                             T* __restrict__ dx, long long total_vec) {
+  constexpr int EPV = 16 / sizeof(T);
+  constexpr int NV = 2 * VW / EPV;
+  const int gv = g.G[2] / VW;
+  const int rows = g.P[0] * g.P[1];            // <= MAXROWS (checked on the host)
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total_vec;
+       o += (long long)gridDim.x * blockDim.x) {
+    long long t = o;
+    int v2 = (int)(t % gv); t /= gv;
+    int g1 = (int)(t % g.G[1]); t /= g.G[1];
+    int g0 = (int)(t % g.G[0]);
+    long long l = t / g.G[0];
+    const long long off = l * g.x_per_lead +
+                          ((long long)(g0 * g.P[0]) * g.X[1] + g1 * g.P[1]) * g.X[2] + v2 * (2 * VW);
+    float4 raw[MAXROWS][NV];
+#pragma unroll
+    for (int r = 0; r < MAXROWS; ++r)
+      if (r < rows) {
+        int p0 = r / g.P[1], p1 = r - p0 * g.P[1];
+        const float4* row = reinterpret_cast<const float4*>(x + off + ((long long)p0 * g.X[1] + p1) * g.X[2]);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) raw[r][k] = __ldg(row + k);
+      }
+    float4 graw;
+    const T* gsrc = dy + l * g.g_per_lead + ((long long)g0 * g.G[1] + g1) * g.G[2] + v2 * VW;
+    if (VW * sizeof(T) == 16) graw = __ldg(reinterpret_cast<const float4*>(gsrc));
+    else *reinterpret_cast<float2*>(&graw) = __ldg(reinterpret_cast<const float2*>(gsrc));
+    const T* gv_ = reinterpret_cast<const T*>(&graw);
+    T best[VW];
+    int arg[VW];
+#pragma unroll
+    for (int r = 0; r < MAXROWS; ++r)
+      if (r < rows) {
+        const T* e = reinterpret_cast<const T*>(raw[r]);
+#pragma unroll
+        for (int w = 0; w < VW; ++w) {
+          T a = e[2 * w], b = e[2 * w + 1];
+          if (r == 0) { best[w] = a; arg[w] = 0; }
+          else if (beats(a, best[w])) { best[w] = a; arg[w] = 2 * r; }
+          if (beats(b, best[w])) { best[w] = b; arg[w] = 2 * r + 1; }
+        }
+      }
+#pragma unroll
+    for (int r = 0; r < MAXROWS; ++r)
+      if (r < rows) {
+        float4 out[NV];
+        T* oe = reinterpret_cast<T*>(out);
+#pragma unroll
+        for (int w = 0; w < VW; ++w) {
+          oe[2 * w] = (arg[w] == 2 * r) ? gv_[w] : (T)0;
+          oe[2 * w + 1] = (arg[w] == 2 * r + 1) ? gv_[w] : (T)0;
+        }
+        int p0 = r / g.P[1], p1 = r - p0 * g.P[1];
+        float4* row = reinterpret_cast<float4*>(dx + off + ((long long)p0 * g.X[1] + p1) * g.X[2]);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) row[k] = out[k];
       }
   }
 }
@@ -232,7 +341,12 @@ int pool_fwd_t(const PoolGeom& g, int mode, const T* x, T* y, cudaStream_t st) {
   int grid = grid_for(total, 256);
   bool pair = mode == 0 && g.P[2] == 2 && g.S[2] == 2 && (g.X[2] % 2 == 0) &&
               ((uintptr_t)x % (2 * sizeof(T)) == 0);
-  if (pair)
+  constexpr int VW = 16 / sizeof(T);   // outputs per thread of the vector kernel: 32 input bytes per row
+  bool vec = pair && (g.X[2] % (2 * VW) == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+  if (vec) {
+    long long tv = total / VW;
+    pool_max_fwd_vec<T, VW><<<grid_for(tv, 256), 256, 0, st>>>(g, x, y, tv);
+  } else if (pair)
     pool_max_fwd_pair<T><<<grid, 256, 0, st>>>(g, x, y, total);
   else if (mode == 0)
     pool_fwd_generic<T, 0><<<grid, 256, 0, st>>>(g, x, y, total);
@@ -250,7 +364,13 @@ int pool_bwd_t(const PoolGeom& g, int mode, const T* dy, const T* x, T* dx, cuda
   bool tiled = g.P[0] == g.S[0] && g.P[1] == g.S[1] && g.P[2] == g.S[2];
   bool pair = mode == 0 && tiled && g.P[2] == 2 && (g.X[2] % 2 == 0) &&
               ((uintptr_t)x % (2 * sizeof(T)) == 0) && ((uintptr_t)dx % (2 * sizeof(T)) == 0);
-  if (pair) {
+  constexpr int VW = 16 / sizeof(T);
+  bool vec = pair && (g.X[2] % (2 * VW) == 0) && g.P[0] * g.P[1] <= 4 && ((uintptr_t)x % 16 == 0) &&
+             ((uintptr_t)dx % 16 == 0) && ((uintptr_t)dy % 16 == 0);
+  if (vec) {
+    long long tv = total_g / VW;
+    pool_max_bwd_tile_vec<T, VW, 4><<<grid_for(tv, 256), 256, 0, st>>>(g, dy, x, dx, tv);
+  } else if (pair) {
     pool_max_bwd_tile_pair<T><<<grid_for(total_g, 256), 256, 0, st>>>(g, dy, x, dx, total_g);
   } else if (mode == 0) {
     pool_bwd_gather<T, 0><<<grid_for(total_x, 256), 256, 0, st>>>(g, dy, x, dx, total_x);
