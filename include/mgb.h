@@ -68,6 +68,23 @@ int mgb_conv_dgrad(const mgb_conv_desc* d, const void* dy, const void* w, void* 
 int mgb_conv_wgrad(const mgb_conv_desc* d, const void* dy, const void* x, void* dw,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* Optional operand cache of the float32 tensor-core path.  That path reads x and dy as
+ * channels-last TF32 hi/lo "planes"; x planes are needed by fwd and wgrad, dy planes by dgrad
+ * and wgrad.  A caller that keeps the planes between calls (as ConvND does between forward
+ * and backward) saves the re-formatting passes.  tensor: 0 = x, 1 = dy.
+ * mgb_conv_planes_bytes reports 0 when the descriptor does not use planes (float64, tiny
+ * channel counts); the *_p entry points accept NULL planes and then behave like the plain ones. */
+int mgb_conv_planes_bytes(const mgb_conv_desc* d, int tensor, size_t* bytes);
+int mgb_conv_make_planes(const mgb_conv_desc* d, int tensor, const void* src, void* planes,
+                         void* stream);
+int mgb_conv_fwd_p(const mgb_conv_desc* d, const void* x, const void* w, void* y,
+                   const void* x_planes, void* ws, size_t ws_bytes, void* stream);
+int mgb_conv_dgrad_p(const mgb_conv_desc* d, const void* dy, const void* w, void* dx,
+                     const void* dy_planes, void* ws, size_t ws_bytes, void* stream);
+int mgb_conv_wgrad_p(const mgb_conv_desc* d, const void* dy, const void* x, void* dw,
+                     const void* dy_planes, const void* x_planes, void* ws, size_t ws_bytes,
+                     void* stream);
+
 /* ---- pooling ----------------------------------------------------------- */
 
 /* Pooling over the trailing `nd` axes of x (lead, X...) -> (lead, G...),

@@ -60,6 +60,11 @@ EXPORTS = {
     "mgb_conv_fwd": (_i, [_cdp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mgb_conv_dgrad": (_i, [_cdp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mgb_conv_wgrad": (_i, [_cdp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mgb_conv_planes_bytes": (_i, [_cdp, _i, C.POINTER(_sz)]),
+    "mgb_conv_make_planes": (_i, [_cdp, _i, _vp, _vp, _vp]),
+    "mgb_conv_fwd_p": (_i, [_cdp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mgb_conv_dgrad_p": (_i, [_cdp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mgb_conv_wgrad_p": (_i, [_cdp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mgb_pool_fwd": (_i, [_pdp, _vp, _vp, _vp]),
     "mgb_pool_bwd": (_i, [_pdp, _vp, _vp, _vp, _vp]),
     "mgb_reduce_broadcast": (_i, [_i, _i, _i64p, _i, _i64p, _vp, _vp, _i, _vp]),
@@ -104,7 +109,7 @@ def _load() -> C.CDLL:
     if not LIB_PATH.exists():
         raise ImportError(
             f"{LIB_PATH} is missing: the CUDA extension has not been built "
-            "(run `python -m mygrad_b200.csrc.build`). mygrad_b200 has no CPU fallback."
+            "(run `python mygrad_b200/csrc/build.py`). mygrad_b200 has no CPU fallback."
         )
     handle = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
     for name, (res, args) in EXPORTS.items():

@@ -1,6 +1,7 @@
 """Builds libmgb200.so (sm_100a) in-tree with nvcc.
 
-Run as ``python -m mygrad_b200.csrc.build`` or through ``__graft_entry__.build()``.
+Run as ``python mygrad_b200/csrc/build.py`` (by path: the package itself refuses to import
+without the library) or through ``__graft_entry__.build()``.
 Objects are cached by source mtime; ``--force`` rebuilds everything.
 """
 from __future__ import annotations

@@ -423,19 +423,22 @@ size_t tc_fwd_ws(const Plan& p) {
   return tc_layout(P.end, p.C, p.F, (int)p.Wp).end;
 }
 
-int tc_fwd(const Plan& p, const float* x, const float* w, float* y, void* ws, size_t ws_bytes,
-           cudaStream_t st) {
+// `planes` (optional): channels-last hi|lo planes made by mgb_conv_make_planes; when null
+// they are built in the workspace.
+int tc_fwd(const Plan& p, const float* x, const float* w, float* y, const void* planes, void* ws,
+           size_t ws_bytes, cudaStream_t st) {
   long long M = p.N * p.Gp;
   if (M * p.F == 0) return 0;
   TcPlanes P = tc_planes(0, p.N, p.C, p.Xp);
   TcLayout L = tc_layout(P.end, p.C, p.F, (int)p.Wp);
   if (ws_bytes < L.end || !ws) return fail("conv fwd: workspace %zu < %zu bytes", ws_bytes, L.end);
   char* base = (char*)ws;
-  float *ahi = (float*)(base + P.hi_off), *alo = (float*)(base + P.lo_off);
+  const char* pl = planes ? (const char*)planes : base;
+  float *ahi = (float*)(pl + P.hi_off), *alo = (float*)(pl + P.lo_off);
   float *bhi = (float*)(base + L.bhi_off), *blo = (float*)(base + L.blo_off);
   tc::TcTap* taps = (tc::TcTap*)(base + L.taps_off);
   int* list = (int*)(base + L.list_off);
-  if (tc_prep_planes(x, ahi, alo, p.N, p.C, p.Xp, P.cpad, st)) return 1;
+  if (!planes && tc_prep_planes(x, ahi, alo, p.N, p.C, p.Xp, P.cpad, st)) return 1;
   TapBuild tb;
   for (int i = 0; i < 3; ++i) {
     tb.cnt[i] = p.W[i]; tb.W[i] = p.W[i]; tb.X[i] = p.X[i];
@@ -468,8 +471,8 @@ size_t tc_dgrad_ws(const Plan& p, const std::vector<DgradClassPlan>& cls) {
   return off;
 }
 
-int tc_dgrad(const Plan& p, const float* dy, const float* w, float* dx, void* ws, size_t ws_bytes,
-             cudaStream_t st) {
+int tc_dgrad(const Plan& p, const float* dy, const float* w, float* dx, const void* planes, void* ws,
+             size_t ws_bytes, cudaStream_t st) {
   long long n_dx = p.N * p.C * p.Xp;
   if (n_dx == 0) return 0;
   std::vector<DgradClassPlan> cls;
@@ -480,8 +483,9 @@ int tc_dgrad(const Plan& p, const float* dy, const float* w, float* dx, void* ws
   if (dgrad_needs_memset(p, cls)) MGB_CUDA(cudaMemsetAsync(dx, 0, (size_t)n_dx * sizeof(float), st));
   char* base = (char*)ws;
   TcPlanes P = tc_planes(0, p.N, p.F, p.Gp);
-  float *ahi = (float*)(base + P.hi_off), *alo = (float*)(base + P.lo_off);
-  if (tc_prep_planes(dy, ahi, alo, p.N, p.F, p.Gp, P.cpad, st)) return 1;
+  const char* pl = planes ? (const char*)planes : base;
+  float *ahi = (float*)(pl + P.hi_off), *alo = (float*)(pl + P.lo_off);
+  if (!planes && tc_prep_planes(dy, ahi, alo, p.N, p.F, p.Gp, P.cpad, st)) return 1;
   size_t off = P.end;
   for (auto& c : cls) {
     TcLayout L = tc_layout(off, p.F, p.C, c.ntap);
@@ -546,21 +550,25 @@ TcWgradLayout tc_wgrad_layout(const Plan& p) {
   return L;
 }
 
-int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes,
-             cudaStream_t st) {
+int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, const void* dy_planes,
+             const void* x_planes, void* ws, size_t ws_bytes, cudaStream_t st) {
   long long n_dw = p.F * p.C * p.Wp;
   if (n_dw == 0) return 0;
   if (p.N * p.Gp == 0) { MGB_CUDA(cudaMemsetAsync(dw, 0, (size_t)n_dw * sizeof(float), st)); return 0; }
   TcWgradLayout L = tc_wgrad_layout(p);
   if (ws_bytes < L.end || !ws) return fail("conv wgrad: workspace %zu < %zu bytes", ws_bytes, L.end);
   char* base = (char*)ws;
-  float *xhi = (float*)(base + L.X.hi_off), *xlo = (float*)(base + L.X.lo_off);
-  float *yhi = (float*)(base + L.Y.hi_off), *ylo = (float*)(base + L.Y.lo_off);
+  // external planes start at offset 0 of their own buffer (tc_planes(0, ...) layout)
+  TcPlanes X0 = tc_planes(0, p.N, p.C, p.Xp), Y0 = tc_planes(0, p.N, p.F, p.Gp);
+  float *xhi = x_planes ? (float*)((char*)x_planes + X0.hi_off) : (float*)(base + L.X.hi_off);
+  float *xlo = x_planes ? (float*)((char*)x_planes + X0.lo_off) : (float*)(base + L.X.lo_off);
+  float *yhi = dy_planes ? (float*)((char*)dy_planes + Y0.hi_off) : (float*)(base + L.Y.hi_off);
+  float *ylo = dy_planes ? (float*)((char*)dy_planes + Y0.lo_off) : (float*)(base + L.Y.lo_off);
   tc::TcTap* taps = (tc::TcTap*)(base + L.taps_off);
   int* list = (int*)(base + L.list_off);
   float* partial = (float*)(base + L.partial_off);
-  if (tc_prep_planes(x, xhi, xlo, p.N, p.C, p.Xp, L.X.cpad, st)) return 1;
-  if (tc_prep_planes(dy, yhi, ylo, p.N, p.F, p.Gp, L.Y.cpad, st)) return 1;
+  if (!x_planes && tc_prep_planes(x, xhi, xlo, p.N, p.C, p.Xp, L.X.cpad, st)) return 1;
+  if (!dy_planes && tc_prep_planes(dy, yhi, ylo, p.N, p.F, p.Gp, L.Y.cpad, st)) return 1;
   TapBuild tb;
   for (int i = 0; i < 3; ++i) {
     tb.cnt[i] = p.W[i]; tb.W[i] = p.W[i]; tb.X[i] = p.X[i];
@@ -718,12 +726,64 @@ extern "C" int mgb_conv_workspace_bytes(const mgb_conv_desc* d, int which, size_
   return 0;
 }
 
+extern "C" int mgb_conv_planes_bytes(const mgb_conv_desc* d, int tensor, size_t* bytes) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (!bytes || (tensor != 0 && tensor != 1)) return fail("mgb_conv_planes_bytes: bad arguments");
+  // x planes feed fwd and wgrad, dy planes feed dgrad and wgrad
+  bool used = tensor == 0 ? (tc_eligible(p, 0) || tc_eligible(p, 2)) : (tc_eligible(p, 1) || tc_eligible(p, 2));
+  *bytes = !used ? 0 : (tensor == 0 ? tc_planes(0, p.N, p.C, p.Xp).end : tc_planes(0, p.N, p.F, p.Gp).end);
+  return 0;
+}
+
+extern "C" int mgb_conv_make_planes(const mgb_conv_desc* d, int tensor, const void* src, void* planes,
+                                    void* stream) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (p.dtype != MGB_F32 || (tensor != 0 && tensor != 1)) return fail("mgb_conv_make_planes: float32 x (0) or dy (1) only");
+  long long ch = tensor == 0 ? p.C : p.F, sp = tensor == 0 ? p.Xp : p.Gp;
+  TcPlanes P = tc_planes(0, p.N, ch, sp);
+  if (p.N * sp == 0) return 0;
+  if (!src || !planes) return fail("mgb_conv_make_planes: null buffer");
+  return tc_prep_planes((const float*)src, (float*)((char*)planes + P.hi_off),
+                        (float*)((char*)planes + P.lo_off), p.N, ch, sp, P.cpad, as_stream(stream));
+}
+
+extern "C" int mgb_conv_fwd_p(const mgb_conv_desc* d, const void* x, const void* w, void* y,
+                              const void* x_planes, void* ws, size_t ws_bytes, void* stream) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (tc_eligible(p, 0))
+    return tc_fwd(p, (const float*)x, (const float*)w, (float*)y, x_planes, ws, ws_bytes, as_stream(stream));
+  return mgb_conv_fwd(d, x, w, y, ws, ws_bytes, stream);
+}
+
+extern "C" int mgb_conv_dgrad_p(const mgb_conv_desc* d, const void* dy, const void* w, void* dx,
+                                const void* dy_planes, void* ws, size_t ws_bytes, void* stream) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (tc_eligible(p, 1))
+    return tc_dgrad(p, (const float*)dy, (const float*)w, (float*)dx, dy_planes, ws, ws_bytes, as_stream(stream));
+  return mgb_conv_dgrad(d, dy, w, dx, ws, ws_bytes, stream);
+}
+
+extern "C" int mgb_conv_wgrad_p(const mgb_conv_desc* d, const void* dy, const void* x, void* dw,
+                                const void* dy_planes, const void* x_planes, void* ws, size_t ws_bytes,
+                                void* stream) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (tc_eligible(p, 2))
+    return tc_wgrad(p, (const float*)dy, (const float*)x, (float*)dw, dy_planes, x_planes, ws, ws_bytes,
+                    as_stream(stream));
+  return mgb_conv_wgrad(d, dy, x, dw, ws, ws_bytes, stream);
+}
+
 extern "C" int mgb_conv_fwd(const mgb_conv_desc* d, const void* x, const void* w, void* y,
                             void* ws, size_t ws_bytes, void* stream) {
   Plan p;
   if (make_plan(d, &p)) return 1;
   if (tc_eligible(p, 0))
-    return tc_fwd(p, (const float*)x, (const float*)w, (float*)y, ws, ws_bytes, as_stream(stream));
+    return tc_fwd(p, (const float*)x, (const float*)w, (float*)y, nullptr, ws, ws_bytes, as_stream(stream));
   if (p.dtype == MGB_F32)
     return fwd_t<float>(p, (const float*)x, (const float*)w, (float*)y, ws, ws_bytes, as_stream(stream));
   return fwd_t<double>(p, (const double*)x, (const double*)w, (double*)y, ws, ws_bytes, as_stream(stream));
@@ -734,7 +794,7 @@ extern "C" int mgb_conv_dgrad(const mgb_conv_desc* d, const void* dy, const void
   Plan p;
   if (make_plan(d, &p)) return 1;
   if (tc_eligible(p, 1))
-    return tc_dgrad(p, (const float*)dy, (const float*)w, (float*)dx, ws, ws_bytes, as_stream(stream));
+    return tc_dgrad(p, (const float*)dy, (const float*)w, (float*)dx, nullptr, ws, ws_bytes, as_stream(stream));
   if (p.dtype == MGB_F32)
     return dgrad_t<float>(p, (const float*)dy, (const float*)w, (float*)dx, ws, ws_bytes, as_stream(stream));
   return dgrad_t<double>(p, (const double*)dy, (const double*)w, (double*)dx, ws, ws_bytes, as_stream(stream));
@@ -745,7 +805,7 @@ extern "C" int mgb_conv_wgrad(const mgb_conv_desc* d, const void* dy, const void
   Plan p;
   if (make_plan(d, &p)) return 1;
   if (tc_eligible(p, 2))
-    return tc_wgrad(p, (const float*)dy, (const float*)x, (float*)dw, ws, ws_bytes, as_stream(stream));
+    return tc_wgrad(p, (const float*)dy, (const float*)x, (float*)dw, nullptr, nullptr, ws, ws_bytes, as_stream(stream));
   if (p.dtype == MGB_F32)
     return wgrad_t<float>(p, (const float*)dy, (const float*)x, (float*)dw, ws, ws_bytes, as_stream(stream));
   return wgrad_t<double>(p, (const double*)dy, (const double*)x, (double*)dw, ws, ws_bytes, as_stream(stream));

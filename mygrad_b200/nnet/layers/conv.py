@@ -30,6 +30,10 @@ _MAX_SPATIAL = 3
 _WORKSPACES: dict = {}
 
 
+def _ptr(a: Optional[DeviceArray]) -> C.c_void_p:
+    return C.c_void_p(a.ptr if a is not None else 0)
+
+
 def _scratch(nbytes: int) -> DeviceArray:
     key = current_stream()
     buf = _WORKSPACES.get(key)
@@ -107,10 +111,23 @@ class ConvND(Operation):
         xin, win = self._operands()
         y = DeviceArray((xd.shape[0], wd.shape[0], *out_shape), self._dtype)
         ws, ws_bytes = self._workspace(0)
-        check(lib.mgb_conv_fwd(C.byref(d), C.c_void_p(xin.ptr), C.c_void_p(win.ptr),
-                               C.c_void_p(y.ptr), C.c_void_p(ws.ptr if ws else 0),
-                               C.c_size_t(ws_bytes), C.c_void_p(current_stream())))
+        # operand cache of the tensor-core path: x planes are re-used by dW, dy planes by dX and dW
+        self._x_planes = self._make_planes(0, xin)
+        self._dy_planes = None
+        check(lib.mgb_conv_fwd_p(C.byref(d), C.c_void_p(xin.ptr), C.c_void_p(win.ptr),
+                                 C.c_void_p(y.ptr), _ptr(self._x_planes), C.c_void_p(ws.ptr if ws else 0),
+                                 C.c_size_t(ws_bytes), C.c_void_p(current_stream())))
         return y
+
+    def _make_planes(self, tensor: int, src: DeviceArray) -> Optional[DeviceArray]:
+        n = C.c_size_t(0)
+        check(lib.mgb_conv_planes_bytes(C.byref(self._desc), tensor, C.byref(n)))
+        if n.value == 0:
+            return None
+        planes = DeviceArray(((n.value + 7) // 8,), np.float64)
+        check(lib.mgb_conv_make_planes(C.byref(self._desc), tensor, C.c_void_p(src.ptr),
+                                       C.c_void_p(planes.ptr), C.c_void_p(current_stream())))
+        return planes
 
     # operands in the compute dtype (mixed f32/f64 inputs are promoted, as NumPy does)
     def _operands(self) -> Tuple[DeviceArray, DeviceArray]:
@@ -132,16 +149,21 @@ class ConvND(Operation):
         if index == 0:  # dX, shape of x, dtype of x (conv.py:118)
             dx = DeviceArray(x.shape, self._dtype)
             ws, ws_bytes = self._workspace(1)
-            check(lib.mgb_conv_dgrad(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(win.ptr),
-                                     C.c_void_p(dx.ptr), C.c_void_p(ws.ptr if ws else 0),
-                                     C.c_size_t(ws_bytes), stream))
+            self._dy_planes = (g.ptr, self._make_planes(1, g))
+            check(lib.mgb_conv_dgrad_p(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(win.ptr),
+                                       C.c_void_p(dx.ptr), _ptr(self._dy_planes[1]),
+                                       C.c_void_p(ws.ptr if ws else 0), C.c_size_t(ws_bytes), stream))
             return dx.astype(x.dtype, copy=False)
         else:  # dW, shape of w
             dw = DeviceArray(w.shape, self._dtype)
             ws, ws_bytes = self._workspace(2)
-            check(lib.mgb_conv_wgrad(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(xin.ptr),
-                                     C.c_void_p(dw.ptr), C.c_void_p(ws.ptr if ws else 0),
-                                     C.c_size_t(ws_bytes), stream))
+            # dy planes made by the dX pass of the same backward call are valid for this grad only
+            cached = getattr(self, "_dy_planes", None)
+            dyp = cached[1] if cached is not None and cached[0] == g.ptr else None
+            check(lib.mgb_conv_wgrad_p(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(xin.ptr),
+                                       C.c_void_p(dw.ptr), _ptr(dyp), _ptr(getattr(self, "_x_planes", None)),
+                                       C.c_void_p(ws.ptr if ws else 0), C.c_size_t(ws_bytes), stream))
+            self._dy_planes = None
             return dw
 
 
