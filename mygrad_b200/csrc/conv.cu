@@ -8,6 +8,7 @@
 
 #include "conv_gemm.cuh"
 #include "conv_tc.cuh"
+#include "conv_tma.cuh"
 
 namespace mgb {
 namespace conv {
@@ -418,6 +419,127 @@ int tc_launch(const tc::TcParams& tp, int ny, cudaStream_t st) {
 
 int pow2_cols(int bn) { int c = 32; while (c < bn) c <<= 1; return c; }
 
+// ---- TMA variant of the fwd-like tensor-core GEMM (conv_tma.cuh) -------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tma_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// MGB_CONV_F32_PATH: "tma" (default) | "cpasync" (cp.async-fed tcgen05 kernel) | "mma"
+bool tma_enabled() {
+  const char* e = getenv("MGB_CONV_F32_PATH");
+  return !(e && (strcmp(e, "cpasync") == 0 || strcmp(e, "mma") == 0));
+}
+
+inline int next_pow2(long long v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+// pixel box (powers of two, 128 pixels) with the fewest tiles; false when no box fits TMA's limits
+bool choose_box(const int P[3], const int pmul[3], long long nbatch, int box[3], int* boxn) {
+  long long best = -1;
+  for (int b0 = 1; b0 <= 128; b0 <<= 1)
+    for (int b1 = 1; b0 * b1 <= 128; b1 <<= 1)
+      for (int b2 = 1; b0 * b1 * b2 <= 128; b2 <<= 1) {
+        int bn = 128 / (b0 * b1 * b2);
+        if (b0 > next_pow2(P[0]) || b1 > next_pow2(P[1]) || b2 > next_pow2(P[2]) || bn > next_pow2(nbatch)) continue;
+        if (b0 * pmul[0] > 256 || b1 * pmul[1] > 256 || b2 * pmul[2] > 256 || bn > 256) continue;
+        long long tiles = ((P[0] + b0 - 1) / b0) * (long long)((P[1] + b1 - 1) / b1) * ((P[2] + b2 - 1) / b2) *
+                          ((nbatch + bn - 1) / bn);
+        // fewer tiles first; then wider contiguous runs for the epilogue stores
+        long long cost = tiles * 1024 - b2;
+        if (best < 0 || cost < best) { best = cost; box[0] = b0; box[1] = b1; box[2] = b2; *boxn = bn; }
+      }
+  return best >= 0;
+}
+
+struct TmaJob {                   // one fwd-like GEMM on channels-last planes
+  const float *a_hi, *a_lo;       // planes [N][X0][X1][X2][cpad]
+  const float *b_hi, *b_lo;       // packed filters [rows][K]
+  const tc::TcTap* taps;
+  float* out;
+  OutMap om;
+  int P[3], pmul[3], base[3], X[3];
+  long long nbatch;
+  int cpad, ntaps, nout, bn, ny, rows;
+};
+
+// returns 0 ok, 1 error, 2 "not applicable, use the cp.async kernel"
+int tma_launch(const TmaJob& j, cudaStream_t st) {
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc || !tma_enabled()) return 2;
+  for (int i = 0; i < 3; ++i) if (j.X[i] < 1) return 2;
+  tma::TmaParams tp;
+  if (!choose_box(j.P, j.pmul, j.nbatch, tp.box, &tp.boxn)) return 2;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)j.cpad, (cuuint64_t)j.X[2], (cuuint64_t)j.X[1], (cuuint64_t)j.X[0],
+                          (cuuint64_t)j.nbatch};
+    cuuint64_t strides[4];
+    strides[0] = (cuuint64_t)j.cpad * 4;
+    strides[1] = strides[0] * j.X[2];
+    strides[2] = strides[1] * j.X[1];
+    strides[3] = strides[2] * j.X[0];
+    cuuint32_t box[5] = {32u, (cuuint32_t)(tp.box[2] * j.pmul[2]), (cuuint32_t)(tp.box[1] * j.pmul[1]),
+                         (cuuint32_t)(tp.box[0] * j.pmul[0]), (cuuint32_t)tp.boxn};
+    cuuint32_t estr[5] = {1u, (cuuint32_t)j.pmul[2], (cuuint32_t)j.pmul[1], (cuuint32_t)j.pmul[0], 1u};
+    CUresult r1 = enc(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)j.a_hi, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)j.a_lo, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return 2;
+  }
+  {
+    long long K = (long long)j.ntaps * j.cpad;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)j.rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {32u, (cuuint32_t)j.bn};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r1 = enc(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)j.b_hi, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&mb_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)j.b_lo, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return 2;
+  }
+  tp.taps = j.taps; tp.out = j.out; tp.om = j.om;
+  long long total = j.ny;
+  for (int i = 0; i < 3; ++i) {
+    tp.P[i] = j.P[i]; tp.pmul[i] = j.pmul[i]; tp.base[i] = j.base[i];
+    tp.tiles[i] = (j.P[i] + tp.box[i] - 1) / tp.box[i];
+    total *= tp.tiles[i];
+  }
+  tp.tiles_n = (int)((j.nbatch + tp.boxn - 1) / tp.boxn);
+  total *= tp.tiles_n;
+  if (total > INT32_MAX) return 2;
+  tp.Nbatch = (int)j.nbatch; tp.Nout = j.nout; tp.nchunk = j.cpad / 32; tp.ntaps = j.ntaps;
+  tp.bn = j.bn; tp.ny = j.ny; tp.tmem_cols = pow2_cols(2 * j.bn); tp.total_tiles = (int)total;
+  constexpr int STAGES = 3;
+  size_t smem = tma::smem_bytes(j.bn, STAGES);
+  MGB_CUDA(cudaFuncSetAttribute(tma::conv_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  int grid = (int)std::min<long long>(total, sm_count());
+  tma::conv_tma_kernel<STAGES><<<grid, tma::THREADS, smem, st>>>(tp, ma_hi, ma_lo, mb_hi, mb_lo);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
 size_t tc_fwd_ws(const Plan& p) {
   TcPlanes P = tc_planes(0, p.N, p.C, p.Xp);
   return tc_layout(P.end, p.C, p.F, (int)p.Wp).end;
@@ -450,6 +572,20 @@ int tc_fwd(const Plan& p, const float* x, const float* w, float* y, const void* 
   tc::PackArgs pa{L.rows, L.cpad, (int)p.F, (int)p.C, (int)p.Wp, L.ntaps, 0};
   tc::pack_filters_split<<<small_grid((long long)L.rows * L.K), 256, 0, st>>>(w, list, bhi, blo, pa);
   MGB_LAUNCH_CHECK();
+  {
+    TmaJob j;
+    j.a_hi = ahi; j.a_lo = alo; j.b_hi = bhi; j.b_lo = blo; j.taps = taps; j.out = y;
+    j.om.sample_stride = p.F * p.Gp; j.om.chan_stride = p.Gp;
+    for (int i = 0; i < 3; ++i) {
+      j.om.omul[i] = 1; j.om.obase[i] = 0;
+      j.P[i] = p.G[i]; j.pmul[i] = p.S[i]; j.base[i] = -p.Pd[i]; j.X[i] = p.X[i];
+    }
+    j.om.os[2] = 1; j.om.os[1] = p.G[2]; j.om.os[0] = p.G[1] * p.G[2];
+    j.nbatch = p.N; j.cpad = P.cpad; j.ntaps = L.ntaps; j.nout = (int)p.F; j.bn = L.bn; j.ny = L.ny;
+    j.rows = L.rows;
+    int rc = tma_launch(j, st);
+    if (rc != 2) return rc;
+  }
   tc::TcParams tp;
   tp.a_hi = ahi; tp.a_lo = alo; tp.taps = taps; tp.b_hi = bhi; tp.b_lo = blo; tp.out = y;
   tp.om.sample_stride = p.F * p.Gp; tp.om.chan_stride = p.Gp;
@@ -504,6 +640,21 @@ int tc_dgrad(const Plan& p, const float* dy, const float* w, float* dx, const vo
     tc::PackArgs pa{L.rows, L.cpad, (int)p.F, (int)p.C, (int)p.Wp, L.ntaps, 1};
     tc::pack_filters_split<<<small_grid((long long)L.rows * L.K), 256, 0, st>>>(w, list, bhi, blo, pa);
     MGB_LAUNCH_CHECK();
+    {
+      TmaJob j;
+      j.a_hi = ahi; j.a_lo = alo; j.b_hi = bhi; j.b_lo = blo; j.taps = taps; j.out = dx;
+      j.om.sample_stride = p.C * p.Xp; j.om.chan_stride = p.Xp;
+      for (int i = 0; i < 3; ++i) {
+        j.om.omul[i] = p.S[i]; j.om.obase[i] = p.S[i] * c.qlo[i] + c.r[i] - p.Pd[i];
+        j.P[i] = c.Q[i]; j.pmul[i] = 1; j.base[i] = c.qlo[i]; j.X[i] = p.G[i];
+      }
+      j.om.os[2] = 1; j.om.os[1] = p.X[2]; j.om.os[0] = p.X[1] * p.X[2];
+      j.nbatch = p.N; j.cpad = P.cpad; j.ntaps = L.ntaps; j.nout = (int)p.C; j.bn = L.bn; j.ny = L.ny;
+      j.rows = L.rows;
+      int rc = tma_launch(j, st);
+      if (rc == 1) return 1;
+      if (rc == 0) continue;
+    }
     tc::TcParams tp;
     tp.a_hi = ahi; tp.a_lo = alo; tp.taps = taps; tp.b_hi = bhi; tp.b_lo = blo; tp.out = dx;
     tp.om.sample_stride = p.C * p.Xp; tp.om.chan_stride = p.Xp;

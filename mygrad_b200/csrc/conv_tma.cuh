@@ -1,0 +1,234 @@
+// FP32 conv fwd / dgrad on tcgen05 with TMA-staged operands (persistent, warp-specialised).
+//
+// Same math and operand format as conv_tc.cuh (3xTF32 over channels-last hi/lo planes), but
+// the shared-memory ring is filled by the Tensor Memory Accelerator instead of cp.async:
+//
+//   * the planes are described to TMA as a rank-5 tensor (Cpad, X2, X1, X0, N); one
+//     `cp.async.bulk.tensor.5d` brings the 32-channel slice of a BOX of 128 pixels
+//     (b2 x b1 x b0 x bn) of one filter tap straight into a K-major SWIZZLE_128B tile.
+//     Tap offsets are coordinate offsets, the conv stride is the map's traversal stride,
+//     and out-of-bounds coordinates are zero-filled by the hardware == zero padding.
+//   * the packed filter bank is a rank-2 tensor (K, rows): one 2-D TMA per plane and stage.
+//   * one thread issues TMA, one thread issues the UMMAs, four warps run the epilogue;
+//     the kernel is persistent (one CTA per SM looping over tiles) and the accumulator is
+//     double-buffered in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
+#pragma once
+#include <cuda.h>
+
+#include "conv_tc.cuh"
+
+namespace mgb {
+namespace conv {
+namespace tma {
+
+using tc::BK;
+using tc::BM;
+
+constexpr int THREADS = 192;            // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int A_TILE_BYTES = BM * 128;
+
+struct TmaParams {
+  const tc::TcTap* taps;                // d0..d2 = coordinate delta of each tap (off unused)
+  float* out;
+  OutMap om;
+  int P[3];                             // pixel grid per sample
+  int pmul[3], base[3];                 // source coord = pixel*pmul + base + tap delta
+  int box[3], boxn;                     // pixels per tile along each spatial axis / batch (powers of two)
+  int tiles[3], tiles_n;                // tile counts
+  int Nbatch, Nout;                     // batch size, real output channels
+  int nchunk, ntaps;
+  int bn, ny;                           // channel tile, number of channel tiles
+  int tmem_cols;
+  int total_tiles;                      // tiles_n*tiles[0]*tiles[1]*tiles[2]*ny
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(tc::smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
+}
+
+inline size_t smem_bytes(int bn, int stages) {
+  return (size_t)stages * (2 * A_TILE_BYTES + 2 * (size_t)bn * 128) + 1024 + 256;
+}
+
+struct TileCoord {
+  int n0, t0, t1, t2, y;   // batch origin, spatial tile indices, channel tile
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TmaParams& p, int tile) {
+  TileCoord c;
+  c.y = tile % p.ny; tile /= p.ny;
+  c.t2 = tile % p.tiles[2]; tile /= p.tiles[2];
+  c.t1 = tile % p.tiles[1]; tile /= p.tiles[1];
+  c.t0 = tile % p.tiles[0]; tile /= p.tiles[0];
+  c.n0 = tile * p.boxn;
+  return c;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(THREADS, 1)
+conv_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUtensorMap map_a_hi,
+                const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_hi,
+                const __grid_constant__ CUtensorMap map_b_lo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = p.bn * 128;
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;    // accumulator buffer ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;        // accumulator buffer drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.ntaps * p.nchunk;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_b_hi); prefetch_tmap(&map_b_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(full_bar + s, 1);
+      tc::mbar_init(empty_bar + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tfull_bar + b, 1);
+      tc::mbar_init(tempty_bar + b, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = tc::smem_u32(smem);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int it = 0;   // ring position, runs across tiles
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tcd = decode_tile(p, tile);
+        const int x0 = tcd.t0 * p.box[0] * p.pmul[0] + p.base[0];
+        const int x1 = tcd.t1 * p.box[1] * p.pmul[1] + p.base[1];
+        const int x2 = tcd.t2 * p.box[2] * p.pmul[2] + p.base[2];
+        for (int s = 0; s < S; ++s, ++it) {
+          const int stage = it % STAGES;
+          if (it >= STAGES) tc::mbar_wait(empty_bar + stage, (uint32_t)((it / STAGES - 1) & 1));
+          const int tap = s / p.nchunk, cc = s - tap * p.nchunk;
+          const int4 tv = __ldg(reinterpret_cast<const int4*>(p.taps) + tap);
+          const uint32_t a_hi = smem_base + stage * stage_bytes;
+          mbar_expect_tx(full_bar + stage, (uint32_t)stage_bytes);
+          tma_load_5d(a_hi, &map_a_hi, full_bar + stage, cc * BK, x2 + tv.w, x1 + tv.z, x0 + tv.y, tcd.n0);
+          tma_load_5d(a_hi + A_TILE_BYTES, &map_a_lo, full_bar + stage, cc * BK, x2 + tv.w, x1 + tv.z,
+                      x0 + tv.y, tcd.n0);
+          tma_load_2d(a_hi + 2 * A_TILE_BYTES, &map_b_hi, full_bar + stage, s * BK, tcd.y * p.bn);
+          tma_load_2d(a_hi + 2 * A_TILE_BYTES + b_tile_bytes, &map_b_lo, full_bar + stage, s * BK,
+                      tcd.y * p.bn);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = tc::idesc_tf32(p.bn);
+      int it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        if (local >= 2) tc::mbar_wait(tempty_bar + buf, (uint32_t)((local / 2 - 1) & 1));
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.bn);
+        for (int s = 0; s < S; ++s, ++it) {
+          const int stage = it % STAGES;
+          tc::mbar_wait(full_bar + stage, (uint32_t)((it / STAGES) & 1));
+          tc::tc_fence_after();
+          const uint32_t a_hi = smem_base + stage * stage_bytes;
+          const uint32_t a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = a_lo + A_TILE_BYTES;
+          const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint64_t dah = tc::smem_desc_k_sw128(a_hi + j * 32), dal = tc::smem_desc_k_sw128(a_lo + j * 32);
+            const uint64_t dbh = tc::smem_desc_k_sw128(b_hi + j * 32), dbl = tc::smem_desc_k_sw128(b_lo + j * 32);
+            tc::umma_tf32(tmem_d, dal, dbh, idesc, (s | j) ? 1u : 0u);
+            tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+          }
+          tc::umma_commit(empty_bar + stage);
+        }
+        tc::umma_commit(tfull_bar + buf);
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;               // tile row == TMEM lane
+    // row -> (in, i0, i1, i2) inside the box (all extents are powers of two)
+    const int i2 = r % p.box[2];
+    const int r1 = r / p.box[2];
+    const int i1 = r1 % p.box[1];
+    const int r0 = r1 / p.box[1];
+    const int i0 = r0 % p.box[0];
+    const int in = r0 / p.box[0];
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const int buf = local & 1;
+      const TileCoord tcd = decode_tile(p, tile);
+      const int n = tcd.n0 + in;
+      const int g0 = tcd.t0 * p.box[0] + i0, g1 = tcd.t1 * p.box[1] + i1, g2 = tcd.t2 * p.box[2] + i2;
+      const bool pv = n < p.Nbatch && g0 < p.P[0] && g1 < p.P[1] && g2 < p.P[2];
+      long long rowoff = -1;
+      if (pv)
+        rowoff = (long long)n * p.om.sample_stride +
+                 (long long)(g0 * p.om.omul[0] + p.om.obase[0]) * p.om.os[0] +
+                 (long long)(g1 * p.om.omul[1] + p.om.obase[1]) * p.om.os[1] +
+                 (long long)(g2 * p.om.omul[2] + p.om.obase[2]) * p.om.os[2];
+      tc::mbar_wait(tfull_bar + buf, (uint32_t)((local / 2) & 1));
+      tc::tc_fence_after();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.bn);
+      const int ch0 = tcd.y * p.bn;
+      for (int col = 0; col < p.bn; col += 16) {
+        uint32_t v[16];
+        tc::tmem_ld16(lane_base + (uint32_t)col, v);
+        if (rowoff >= 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            int ch = ch0 + col + j;
+            if (ch < p.Nout) p.out[rowoff + (long long)ch * p.om.chan_stride] = __uint_as_float(v[j]);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(tempty_bar + buf);             // 128 arrivals free the accumulator buffer
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace tma
+}  // namespace conv
+}  // namespace mgb

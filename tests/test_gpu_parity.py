@@ -214,9 +214,9 @@ TC_CASES = [
 
 
 @pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "x".join(map(str, c[:3])) + f"_{len(c[3])}d")
-@pytest.mark.parametrize("path", ["tc", "mma"])
+@pytest.mark.parametrize("path", ["tma", "cpasync", "mma"])
 def test_conv_f32_paths_vs_oracle(case, path, monkeypatch):
-    """both fp32 kernels (tcgen05 3xTF32 and the mma.sync fallback) against the oracle"""
+    """every fp32 kernel family (tcgen05 fed by TMA, tcgen05 fed by cp.async, mma.sync) against the oracle"""
     monkeypatch.setenv("MGB_CONV_F32_PATH", path)
     N, C, F, X, W, s, p, d = case
     rng = np.random.default_rng(hash(case) % (2 ** 32))
