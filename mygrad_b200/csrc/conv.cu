@@ -449,12 +449,13 @@ bool tma_enabled() {
 inline int next_pow2(long long v) { int r = 1; while (r < v) r <<= 1; return r; }
 
 // pixel box (powers of two, 128 pixels) with the fewest tiles; false when no box fits TMA's limits
-bool choose_box(const int P[3], const int pmul[3], long long nbatch, int box[3], int* boxn) {
+bool choose_box(const int P[3], const int pmul[3], long long nbatch, int box[3], int* boxn,
+                int pixels = 128) {
   long long best = -1;
-  for (int b0 = 1; b0 <= 128; b0 <<= 1)
-    for (int b1 = 1; b0 * b1 <= 128; b1 <<= 1)
-      for (int b2 = 1; b0 * b1 * b2 <= 128; b2 <<= 1) {
-        int bn = 128 / (b0 * b1 * b2);
+  for (int b0 = 1; b0 <= pixels; b0 <<= 1)
+    for (int b1 = 1; b0 * b1 <= pixels; b1 <<= 1)
+      for (int b2 = 1; b0 * b1 * b2 <= pixels; b2 <<= 1) {
+        int bn = pixels / (b0 * b1 * b2);
         if (b0 > next_pow2(P[0]) || b1 > next_pow2(P[1]) || b2 > next_pow2(P[2]) || bn > next_pow2(nbatch)) continue;
         if (b0 * pmul[0] > 256 || b1 * pmul[1] > 256 || b2 * pmul[2] > 256 || bn > 256) continue;
         long long tiles = ((P[0] + b0 - 1) / b0) * (long long)((P[1] + b1 - 1) / b1) * ((P[2] + b2 - 1) / b2) *
@@ -674,6 +675,7 @@ int tc_dgrad(const Plan& p, const float* dy, const float* w, float* dx, const vo
 struct TcWgradLayout {
   TcPlanes X, Y;            // channels-last planes of x and dy
   int cblocks, nblocks, nt, nbpc, mt, splits, kps;
+  int tma_splits;           // split count of the TMA variant (boxes of 16 pixels)
   size_t taps_off, list_off, partial_off, end;
 };
 
@@ -696,9 +698,85 @@ TcWgradLayout tc_wgrad_layout(const Plan& p) {
   size_t off = align_up(L.Y.end, 256);
   L.taps_off = off; off += align_up((size_t)p.Wp * sizeof(tc::TcTap), 256);
   L.list_off = off; off += align_up((size_t)p.Wp * sizeof(int), 256);
-  L.partial_off = off; off += align_up((size_t)L.splits * p.F * p.C * p.Wp * sizeof(float), 256);
+  L.tma_splits = std::max(1, sm_count() / (L.mt * L.nt));
+  L.partial_off = off;
+  off += align_up((size_t)std::max(L.splits, L.tma_splits) * p.F * p.C * p.Wp * sizeof(float), 256);
   L.end = off;
   return L;
+}
+
+// returns 0 ok, 1 error, 2 not applicable
+int wgrad_tma_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const float* xlo, const float* yhi,
+                     const float* ylo, const tc::TcTap* taps, float* partial, cudaStream_t st) {
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc || !tma_enabled()) return 2;
+  for (int i = 0; i < 3; ++i) if (p.X[i] < 1 || p.G[i] < 1) return 2;
+  tma::WgradTmaParams wp;
+  // blocked maps need the channel-block axis as a fifth dimension: <= 2 spatial dims, and the
+  // CTA's (tap, c-block) ranges must be whole taps
+  wp.blocked = (p.X[0] == 1 && p.G[0] == 1 && L.nbpc % L.cblocks == 0) ? 1 : 0;
+  wp.pix = wp.blocked ? 32 : tma::WG_PIX;
+  if (!choose_box(p.G, p.S, p.N, wp.box, &wp.boxn, wp.pix)) return 2;
+  CUtensorMap mdy_hi, mdy_lo, mx_hi, mx_lo;
+  auto encode = [&](CUtensorMap* m, const float* base, int cpad, const int X[3], const int mul[3], int nblk) {
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5];
+    if (wp.blocked) {   // (32, X2, X1, N, cpad/32)
+      dims[0] = 32; dims[1] = X[2]; dims[2] = X[1]; dims[3] = p.N; dims[4] = cpad / 32;
+      strides[0] = (cuuint64_t)cpad * 4; strides[1] = strides[0] * X[2]; strides[2] = strides[1] * X[1];
+      strides[3] = 128;
+      box[0] = 32; box[1] = wp.box[2] * mul[2]; box[2] = wp.box[1] * mul[1]; box[3] = wp.boxn; box[4] = nblk;
+      estr[0] = 1; estr[1] = mul[2]; estr[2] = mul[1]; estr[3] = 1; estr[4] = 1;
+    } else {            // (cpad, X2, X1, X0, N)
+      dims[0] = cpad; dims[1] = X[2]; dims[2] = X[1]; dims[3] = X[0]; dims[4] = p.N;
+      strides[0] = (cuuint64_t)cpad * 4; strides[1] = strides[0] * X[2]; strides[2] = strides[1] * X[1];
+      strides[3] = strides[2] * X[0];
+      box[0] = 32; box[1] = wp.box[2] * mul[2]; box[2] = wp.box[1] * mul[1]; box[3] = wp.box[0] * mul[0];
+      box[4] = wp.boxn;
+      estr[0] = 1; estr[1] = mul[2]; estr[2] = mul[1]; estr[3] = mul[0]; estr[4] = 1;
+    }
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  const int one[3] = {1, 1, 1};
+  if (!encode(&mdy_hi, yhi, L.Y.cpad, p.G, one, 4) || !encode(&mdy_lo, ylo, L.Y.cpad, p.G, one, 4) ||
+      !encode(&mx_hi, xhi, L.X.cpad, p.X, p.S, L.cblocks) || !encode(&mx_lo, xlo, L.X.cpad, p.X, p.S, L.cblocks))
+    return 2;
+  long long boxes = 1;
+  for (int i = 0; i < 3; ++i) {
+    wp.tiles[i] = (p.G[i] + wp.box[i] - 1) / wp.box[i];
+    wp.S[i] = p.S[i]; wp.Pd[i] = p.Pd[i];
+    boxes *= wp.tiles[i];
+  }
+  wp.tiles_n = (int)((p.N + wp.boxn - 1) / wp.boxn);
+  boxes *= wp.tiles_n;
+  if (boxes > INT32_MAX) return 2;
+  int splits = (int)std::max<long long>(1, std::min<long long>(L.tma_splits, boxes / 8));
+  long long per = (boxes + splits - 1) / splits;
+  splits = (int)((boxes + per - 1) / per);
+  L.tma_splits = splits;
+  wp.taps = taps; wp.partial = partial;
+  wp.F = (int)p.F; wp.C = (int)p.C; wp.Wp = (int)p.Wp; wp.cblocks = L.cblocks;
+  wp.nblocks_total = L.nblocks; wp.nbpc = L.nbpc;
+  wp.boxes_total = (int)boxes; wp.boxes_per_split = (int)per;
+  wp.tmem_cols = pow2_cols(L.nbpc * 32);
+  dim3 grid(L.mt, L.nt, splits);
+  if (wp.pix == 32) {
+    constexpr int STAGES = 2;
+    size_t smem = tma::wgrad_smem_bytes(L.nbpc, STAGES, wp.pix);
+    MGB_CUDA(cudaFuncSetAttribute(tma::wgrad_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    tma::wgrad_tma_kernel<STAGES><<<grid, tma::THREADS, smem, st>>>(wp, mdy_hi, mdy_lo, mx_hi, mx_lo);
+  } else {
+    constexpr int STAGES = 4;
+    size_t smem = tma::wgrad_smem_bytes(L.nbpc, STAGES, wp.pix);
+    MGB_CUDA(cudaFuncSetAttribute(tma::wgrad_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    tma::wgrad_tma_kernel<STAGES><<<grid, tma::THREADS, smem, st>>>(wp, mdy_hi, mdy_lo, mx_hi, mx_lo);
+  }
+  MGB_LAUNCH_CHECK();
+  return 0;
 }
 
 int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, const void* dy_planes,
@@ -735,6 +813,16 @@ int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, const vo
   for (int i = 0; i < 3; ++i) { wp.G[i] = p.G[i]; wp.S[i] = p.S[i]; wp.Pd[i] = p.Pd[i]; wp.X[i] = p.X[i]; }
   wp.gp = (int)p.Gp; wp.Ktot = (int)(p.N * p.Gp); wp.k_per_split = L.kps;
   wp.nblocks_total = L.nblocks; wp.nbpc = L.nbpc; wp.tmem_cols = pow2_cols(L.nbpc * 32);
+  // TMA-staged variant first; the cp.async kernel is the fallback
+  {
+    int rc = wgrad_tma_launch(p, L, xhi, xlo, yhi, ylo, taps, partial, st);
+    if (rc == 1) return 1;
+    if (rc == 0) {
+      splitk_reduce<float><<<small_grid(n_dw), 256, 0, st>>>(partial, dw, n_dw, L.tma_splits);
+      MGB_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   constexpr int STAGES = 4;
   size_t smem = tc::wgrad_smem_bytes(L.nbpc, STAGES);
   MGB_CUDA(cudaFuncSetAttribute(tc::wgrad_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -229,6 +229,183 @@ conv_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUt
   if (warp == 1) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ---- wgrad with TMA-staged MN-major operands -------------------------------------------------
+//
+// K = output pixels, walked box by box (b2 x b1 x b0 x bn = 16 pixels per stage); for each
+// box one TMA per 32-channel block brings [16 pixels][32 channels] of dy (A) and of the
+// tap-shifted x (B) into SWIZZLE_128B_ATOM_32B tiles = UMMA's SWIZZLE_128B_BASE32B.
+// Out-of-range pixels (ragged boxes, padding) arrive as zeros and contribute nothing.
+
+constexpr int WG_PIX = 16;                 // pixels per stage of the un-blocked flavour
+
+struct WgradTmaParams {
+  const tc::TcTap* taps;                   // d0..d2 = k*dil per tap
+  float* partial;                          // [splits][F][C][Wp]
+  int box[3], boxn;                        // 16-pixel box (powers of two)
+  int tiles[3], tiles_n;                   // boxes per axis
+  int S[3], Pd[3];                         // conv stride / padding
+  int F, C, Wp, cblocks, nblocks_total, nbpc;
+  int boxes_total, boxes_per_split;
+  int tmem_cols;
+  int pix;                                 // pixels per stage: 16 or 32
+  // "blocked" tensor maps (<= 2 spatial dims): the channel axis is split into (32, block) and
+  // the block index is the slowest box dimension, so ONE TMA brings several 32-channel
+  // blocks ([block][pixel][128 B], exactly the UMMA operand order): 4 f-blocks of dy, and
+  // all c-blocks of one tap of x.  Small boxes are what limits TMA here, not bytes.
+  int blocked;
+};
+
+inline size_t wgrad_smem_bytes(int nbpc, int stages, int pix) {
+  return (size_t)stages * (2 * 4 * (size_t)pix * 128 + 2 * (size_t)nbpc * pix * 128) + 1024 + 256;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(THREADS, 1)
+wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant__ CUtensorMap map_dy_hi,
+                 const __grid_constant__ CUtensorMap map_dy_lo, const __grid_constant__ CUtensorMap map_x_hi,
+                 const __grid_constant__ CUtensorMap map_x_lo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int WG_BLK_BYTES = p.pix * 128;                 // one 32-channel block of one plane
+  const int a_plane = 4 * WG_BLK_BYTES;                 // 128 f-channels
+  const int b_plane = p.nbpc * WG_BLK_BYTES;
+  const int stage_bytes = 2 * a_plane + 2 * b_plane;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+  const int blk0 = blockIdx.y * p.nbpc;
+  const int nvalid = min(p.nbpc, p.nblocks_total - blk0);     // (tap, c-block) blocks of this CTA
+  const int kb0 = blockIdx.z * p.boxes_per_split;
+  const int kb1 = min(p.boxes_total, kb0 + p.boxes_per_split);
+  const int S = max(0, kb1 - kb0);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_dy_hi); prefetch_tmap(&map_dy_lo); prefetch_tmap(&map_x_hi); prefetch_tmap(&map_x_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(full_bar + s, 1);
+      tc::mbar_init(empty_bar + s, 1);
+    }
+    tc::mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = tc::smem_u32(smem);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      const uint32_t tx = (uint32_t)(2 * a_plane + 2 * nvalid * WG_BLK_BYTES);
+      for (int s = 0; s < S; ++s) {
+        const int stage = s % STAGES;
+        if (s >= STAGES) tc::mbar_wait(empty_bar + stage, (uint32_t)((s / STAGES - 1) & 1));
+        int kb = kb0 + s;
+        const int t2 = kb % p.tiles[2]; kb /= p.tiles[2];
+        const int t1 = kb % p.tiles[1]; kb /= p.tiles[1];
+        const int t0 = kb % p.tiles[0]; kb /= p.tiles[0];
+        const int n0 = kb * p.boxn;
+        const int g0 = t0 * p.box[0], g1 = t1 * p.box[1], g2 = t2 * p.box[2];
+        const uint32_t a_hi = smem_base + stage * stage_bytes;
+        mbar_expect_tx(full_bar + stage, tx);
+        const uint32_t b_hi = a_hi + 2 * a_plane;
+        const int x0 = g0 * p.S[0] - p.Pd[0], x1 = g1 * p.S[1] - p.Pd[1], x2 = g2 * p.S[2] - p.Pd[2];
+        if (p.blocked) {
+          // coordinates (ch-in-block, x2, x1, n, block)
+          tma_load_5d(a_hi, &map_dy_hi, full_bar + stage, 0, g2, g1, n0, m0 / 32);
+          tma_load_5d(a_hi + a_plane, &map_dy_lo, full_bar + stage, 0, g2, g1, n0, m0 / 32);
+          for (int b = 0; b < nvalid; b += p.cblocks) {
+            const int tap = (blk0 + b) / p.cblocks;
+            const int4 tv = __ldg(reinterpret_cast<const int4*>(p.taps) + tap);
+            tma_load_5d(b_hi + b * WG_BLK_BYTES, &map_x_hi, full_bar + stage, 0, x2 + tv.w, x1 + tv.z, n0, 0);
+            tma_load_5d(b_hi + b_plane + b * WG_BLK_BYTES, &map_x_lo, full_bar + stage, 0, x2 + tv.w,
+                        x1 + tv.z, n0, 0);
+          }
+        } else {
+          for (int mb = 0; mb < 4; ++mb) {
+            tma_load_5d(a_hi + mb * WG_BLK_BYTES, &map_dy_hi, full_bar + stage, m0 + mb * 32, g2, g1, g0, n0);
+            tma_load_5d(a_hi + a_plane + mb * WG_BLK_BYTES, &map_dy_lo, full_bar + stage, m0 + mb * 32, g2,
+                        g1, g0, n0);
+          }
+          for (int b = 0; b < nvalid; ++b) {
+            const int gb = blk0 + b;
+            const int tap = gb / p.cblocks, cb = gb - tap * p.cblocks;
+            const int4 tv = __ldg(reinterpret_cast<const int4*>(p.taps) + tap);
+            tma_load_5d(b_hi + b * WG_BLK_BYTES, &map_x_hi, full_bar + stage, cb * 32, x2 + tv.w, x1 + tv.z,
+                        x0 + tv.y, n0);
+            tma_load_5d(b_hi + b_plane + b * WG_BLK_BYTES, &map_x_lo, full_bar + stage, cb * 32, x2 + tv.w,
+                        x1 + tv.z, x0 + tv.y, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer: A and B MN-major, N = nvalid*32 =====
+      const uint32_t idesc = tc::idesc_tf32(nvalid * 32) | (1u << 15) | (1u << 16);
+      for (int s = 0; s < S; ++s) {
+        const int stage = s % STAGES;
+        tc::mbar_wait(full_bar + stage, (uint32_t)((s / STAGES) & 1));
+        tc::tc_fence_after();
+        const uint32_t a_hi = smem_base + stage * stage_bytes;
+        const uint32_t a_lo = a_hi + a_plane;
+        const uint32_t b_hi = a_lo + a_plane;
+        const uint32_t b_lo = b_hi + b_plane;
+        for (int j = 0; j < p.pix / 8; ++j) {
+          // block (32 channels) stride = pix*128 B (LBO), 4-pixel k-atom stride = 512 B (SBO)
+          const uint64_t dah = tc::smem_desc_mn_sw128(a_hi + j * 1024, (uint32_t)WG_BLK_BYTES, 512u);
+          const uint64_t dal = tc::smem_desc_mn_sw128(a_lo + j * 1024, (uint32_t)WG_BLK_BYTES, 512u);
+          const uint64_t dbh = tc::smem_desc_mn_sw128(b_hi + j * 1024, (uint32_t)WG_BLK_BYTES, 512u);
+          const uint64_t dbl = tc::smem_desc_mn_sw128(b_lo + j * 1024, (uint32_t)WG_BLK_BYTES, 512u);
+          tc::umma_tf32(tmem_base, dal, dbh, idesc, (s | j) ? 1u : 0u);
+          tc::umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          tc::umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        tc::umma_commit(empty_bar + stage);
+      }
+      if (S > 0) tc::umma_commit(accum_bar);
+    }
+  } else {
+    // ===== epilogue: lane = f, columns = (block, channel) -> partial[f][c][tap] =====
+    const int quarter = warp & 3;
+    const int f = m0 + quarter * 32 + lane;
+    float* out = p.partial + (long long)blockIdx.z * p.F * p.C * p.Wp;
+    if (S > 0) {
+      tc::mbar_wait(accum_bar, 0);
+      tc::tc_fence_after();
+    }
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int col = 0; col < nvalid * 32; col += 16) {
+      uint32_t v[16];
+      if (S > 0) {
+        tc::tmem_ld16(lane_base + (uint32_t)col, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      const int gb = blk0 + (col >> 5);
+      const int tap = gb / p.cblocks, cb = gb - tap * p.cblocks;
+      if (f < p.F) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int c = cb * 32 + (col & 31) + j;
+          if (c < p.C) out[((long long)f * p.C + c) * p.Wp + tap] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 }  // namespace tma
 }  // namespace conv
 }  // namespace mgb
