@@ -307,34 +307,35 @@ def run_ours(args, cfg, name):
     # ---- end to end with host buffers ------------------------------------------------------
     e2e = None
     if not args.no_e2e:
+        # the host-buffer API: pinned NumPy in, pinned NumPy out, batch chunks pipelined over
+        # H2D / compute / D2H streams (mygrad_b200/host.py)
         px, pw = mg.pinned_empty(cfg["x"], dt), mg.pinned_empty(cfg["w"], dt)
         px[...] = xh; pw[...] = wh
-        o, xt, wt = step(x_dev, w_dev)
-        po = mg.pinned_empty(o.shape, dt)
-        pdx, pdw = mg.pinned_empty(cfg["x"], dt), mg.pinned_empty(cfg["w"], dt)
-        xd2, wd2 = mg.empty(cfg["x"], dt), mg.empty(cfg["w"], dt)
+        pipe = mg.HostLayerPipeline(pool=cfg["pool"], pool_stride=2, chunks=args.e2e_chunks, **conv_kw)
+        dw_all = []
 
         def e2e_step():
-            xd2.set_from_host(px, sync=False)
-            wd2.set_from_host(pw, sync=False)
-            o, xt, wt = step(xd2, wd2)
-            o.data.get(po, sync=False)
-            xt.grad.get(pdx, sync=False)
-            wt.grad.get(pdw, sync=False)
-            mg.synchronize()
+            o, dx_h, dw_h = pipe.step(px, pw)
+            if world > 1:   # dW of the host API is per rank; sum it like the device path does
+                g = mg.asdevice(dw_h)
+                dp.allreduce([g])
+                g.get(dw_h)
+            return o, dx_h, dw_h
 
         for _ in range(2):
-            e2e_step()
+            res = e2e_step()
         barrier()
         ke = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(ke):
-            e2e_step()
+            res = e2e_step()
         barrier()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / ke)
         e2e = {"value": world * batch / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(px.nbytes + pw.nbytes),
-               "d2h_bytes_per_step": int(po.nbytes + pdx.nbytes + pdw.nbytes)}
+               "d2h_bytes_per_step": int(sum(r.nbytes for r in res)),
+               "api": f"HostLayerPipeline.step (chunks={args.e2e_chunks}; H2D/compute/D2H overlapped)"}
+        pipe.close()
 
     # ---- per-phase timing: which kernel dominates, and its roofline -------------------------
     # (straight through the C ABI with preallocated outputs, so that only kernels are timed)
@@ -458,6 +459,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -31,6 +31,7 @@ from .errors import DisconnectedView, InvalidBackprop, InvalidGradient, SkipGrad
 from .operation_base import Operation
 from .tensor_base import Tensor, asarray, tensor
 from . import nnet
+from .host import HostLayerPipeline
 from .nnet.layers import conv_nd, max_pool, mean_pool
 
 execute_op = Tensor._op  # same alias as mygrad.execute_op (src/mygrad/__init__.py:52)
@@ -42,5 +43,5 @@ __all__ = [
     "DeviceArray", "asdevice", "empty", "zeros", "full", "full_like", "pinned_empty",
     "current_stream", "set_stream", "synchronize", "device_available", "empty_cache",
     "InvalidGradient", "InvalidBackprop", "DisconnectedView", "SkipGradient",
-    "nnet", "conv_nd", "max_pool", "mean_pool", "lib", "LIB_PATH",
+    "nnet", "conv_nd", "max_pool", "mean_pool", "HostLayerPipeline", "lib", "LIB_PATH",
 ]

@@ -212,3 +212,27 @@ def test_launch_counter_counts_kernels():
     mg.full((1024,), 1.0, np.float32)
     lib.mgb_launch_count(C.byref(after))
     assert after.value == before.value + 1
+
+
+def test_host_pipeline_matches_single_pass():
+    """chunked H2D/compute/D2H pipeline == one pass over the whole batch (dW is additive)"""
+    rng = np.random.default_rng(9)
+    for dt, chunks in ((np.float32, 3), (np.float64, 4), (np.float32, 16)):
+        xh = rng.standard_normal((10, 16, 12, 12)).astype(dt)
+        wh = rng.standard_normal((24, 16, 3, 3)).astype(dt)
+        px, pw = mg.pinned_empty(xh.shape, dt), mg.pinned_empty(wh.shape, dt)
+        px[...] = xh; pw[...] = wh
+        pipe = mg.HostLayerPipeline(stride=1, padding=1, pool=(2, 2), pool_stride=2, chunks=chunks)
+        out, dx, dw = pipe.step(px, pw)
+        x, w = Tensor(xh), Tensor(wh)
+        o = max_pool(conv_nd(x, w, stride=1, padding=1), (2, 2), 2)
+        o.backward()
+        np.testing.assert_array_equal(out, o.numpy())          # per-sample work: identical
+        np.testing.assert_array_equal(dx, x.grad.get())
+        assert_close(dw, w.grad.get(), dt)
+        want_out, want_dx, want_dw = oc.layer_step(xh, wh, stride=1, padding=1, dilation=1,
+                                                   pool=(2, 2), pool_stride=2)
+        assert_close(out, want_out, dt); assert_close(dx, want_dx, dt); assert_close(dw, want_dw, dt)
+        out2, _, _ = pipe.step(px, pw)                          # buffers are re-usable
+        np.testing.assert_array_equal(out2, o.numpy())
+        pipe.close()
