@@ -131,6 +131,29 @@ int mgb_fill(int dtype, size_t n, double value, void* dst, void* stream);
 /* dst[i] *= alpha — used by the data-parallel wrapper (1/R for mean losses) */
 int mgb_scale(int dtype, size_t n, double alpha, void* dst, void* stream);
 
+/* ---- ops around the path (what a small CNN needs so that a whole
+ *      Tensor.backward stays on the device; all bandwidth-bound or tiny) ------------- */
+
+/* y = x * (x > 0)   — ReLu.__call__ (src/mygrad/nnet/activations/relu.py:10-14) */
+int mgb_relu_fwd(int dtype, size_t n, const void* x, void* y, void* stream);
+/* dx = grad * (x > 0) — ReLu.backward_var (relu.py:16-17) */
+int mgb_relu_bwd(int dtype, size_t n, const void* grad, const void* x, void* dx, void* stream);
+/* out = a + b with NumPy broadcasting; the three shapes are given at the output rank
+ * (ones prepended) — Add.__call__ (src/mygrad/math/arithmetic/ops.py:28-32) */
+int mgb_add_broadcast(int dtype, int ndim, const int64_t* out_shape, const int64_t* a_shape,
+                      const int64_t* b_shape, const void* a, const void* b, void* out, void* stream);
+/* dst (cols, rows) = src (rows, cols)^T — operand packing for MatMul run as a 1x1 convolution
+ * (src/mygrad/math/misc/ops.py:91-127) */
+int mgb_transpose2d(int dtype, int64_t rows, int64_t cols, const void* src, void* dst, void* stream);
+/* loss = mean_n(-log softmax(x)[n, label_n]); back = (softmax(x) - onehot)/N (may be NULL).
+ * labels are class indices stored in the tensor dtype.
+ * SoftmaxCrossEntropy.__call__ (src/mygrad/nnet/losses/softmax_crossentropy.py:14-50),
+ * logsumexp (src/mygrad/math/_special.py:4-68) */
+int mgb_softmax_xent(int dtype, int64_t n, int64_t c, const void* x, const void* labels, void* loss,
+                     void* back, void* stream);
+/* dst[i] = (*scalar) * src[i], scalar on the device — `grad * self.back` (softmax_crossentropy.py:50) */
+int mgb_scale_by(int dtype, size_t n, const void* scalar, const void* src, void* dst, void* stream);
+
 /* ---- runtime plumbing -------------------------------------------------- */
 
 int mgb_device_count(int* count);

@@ -72,6 +72,12 @@ EXPORTS = {
     "mgb_copy_cast": (_i, [_i, _i, _sz, _vp, _vp, _vp]),
     "mgb_fill": (_i, [_i, _sz, C.c_double, _vp, _vp]),
     "mgb_scale": (_i, [_i, _sz, C.c_double, _vp, _vp]),
+    "mgb_relu_fwd": (_i, [_i, _sz, _vp, _vp, _vp]),
+    "mgb_relu_bwd": (_i, [_i, _sz, _vp, _vp, _vp, _vp]),
+    "mgb_add_broadcast": (_i, [_i, _i, _i64p, _i64p, _i64p, _vp, _vp, _vp, _vp]),
+    "mgb_transpose2d": (_i, [_i, C.c_int64, C.c_int64, _vp, _vp, _vp]),
+    "mgb_softmax_xent": (_i, [_i, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "mgb_scale_by": (_i, [_i, _sz, _vp, _vp, _vp, _vp]),
     "mgb_device_count": (_i, [C.POINTER(_i)]),
     "mgb_set_device": (_i, [_i]),
     "mgb_get_device": (_i, [C.POINTER(_i)]),

@@ -178,7 +178,8 @@ class DeviceArray:
     # ---- construction / transfer -------------------------------------------------
     @classmethod
     def from_numpy(cls, arr: np.ndarray) -> "DeviceArray":
-        arr = np.ascontiguousarray(arr)
+        if not arr.flags["C_CONTIGUOUS"]:
+            arr = np.ascontiguousarray(arr)   # (0-d arrays are contiguous; ascontiguousarray would make them 1-d)
         out = cls(arr.shape, arr.dtype)
         if arr.size:
             check(lib.mgb_memcpy_h2d(C.c_void_p(out.ptr), C.c_void_p(arr.ctypes.data),

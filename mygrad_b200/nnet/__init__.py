@@ -1,5 +1,7 @@
 """Neural-network layers of the device path (mirrors ``mygrad.nnet``)."""
-from . import layers
+from . import activations, layers, losses
+from .activations import relu
+from .losses import softmax_crossentropy
 from .layers import conv_nd, max_pool, mean_pool
 
-__all__ = ["layers", "conv_nd", "max_pool", "mean_pool"]
+__all__ = ["layers", "activations", "losses", "conv_nd", "max_pool", "mean_pool", "relu", "softmax_crossentropy"]

@@ -232,6 +232,27 @@ class Tensor:
         if self._creator is not None:
             self._creator.backward(self._grad)
 
+    # ---- the little operator sugar config 5 uses (everything else is out of scope) -----
+    def __add__(self, other) -> "Tensor":
+        from .math_ops import add
+
+        return add(self, other)
+
+    def __radd__(self, other) -> "Tensor":
+        from .math_ops import add
+
+        return add(other, self)
+
+    def __matmul__(self, other) -> "Tensor":
+        from .math_ops import matmul
+
+        return matmul(self, other)
+
+    def reshape(self, *newshape) -> "Tensor":
+        from .math_ops import reshape
+
+        return reshape(self, *newshape)
+
     def null_grad(self) -> "Tensor":
         self._grad = None
         return self

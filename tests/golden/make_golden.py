@@ -218,3 +218,40 @@ if __name__ == "__main__":
     print("graph cases:", run_graph_cases())
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")
+
+
+# ---- config-5-like small CNN through the reference (scaled down) -----------
+def run_cnn_case():
+    from mygrad.nnet.activations import relu
+    from mygrad.nnet.losses import softmax_crossentropy
+
+    r = np.random.default_rng(21)
+    out = {}
+    for tag, dt in (("f32", "f4"), ("f64", "f8")):
+        x = r.standard_normal((8, 3, 16, 16)).astype(dt)
+        labels = r.integers(0, 10, 8)
+        w1 = (r.standard_normal((16, 3, 3, 3)) * 0.1).astype(dt)
+        b1 = (r.standard_normal((1, 16, 1, 1)) * 0.1).astype(dt)
+        w2 = (r.standard_normal((32, 16, 3, 3)) * 0.05).astype(dt)
+        b2 = (r.standard_normal((1, 32, 1, 1)) * 0.1).astype(dt)
+        wd = (r.standard_normal((32 * 4 * 4, 10)) * 0.01).astype(dt)
+        bd = (r.standard_normal((10,)) * 0.1).astype(dt)
+        params = {k: mg.Tensor(v) for k, v in dict(w1=w1, b1=b1, w2=w2, b2=b2, wd=wd, bd=bd).items()}
+        xt = mg.Tensor(x)
+        h = max_pool(relu(conv_nd(xt, params["w1"], stride=1, padding=1) + params["b1"]), (2, 2), 2)
+        h = max_pool(relu(conv_nd(h, params["w2"], stride=1, padding=1) + params["b2"]), (2, 2), 2)
+        logits = h.reshape(8, -1) @ params["wd"] + params["bd"]
+        loss = softmax_crossentropy(logits, labels)
+        loss.backward()
+        out[f"{tag}/x"], out[f"{tag}/labels"] = x, labels
+        out[f"{tag}/loss"], out[f"{tag}/logits"], out[f"{tag}/dx"] = loss.data, logits.data, xt.grad
+        for k, t in params.items():
+            out[f"{tag}/{k}"], out[f"{tag}/d{k}"] = t.data, t.grad
+    np.savez_compressed(HERE / "cnn_case.npz", **out)
+    return 2
+
+
+if __name__ == "__main__":
+    print("cnn cases:", run_cnn_case())
+    for f in sorted(HERE.glob("cnn*.npz")):
+        print(f.name, f.stat().st_size, "bytes")
