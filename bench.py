@@ -45,6 +45,8 @@ WORKLOADS = {
     "C3": dict(x=(128, 128, 65, 65), w=(256, 128, 5, 5), stride=2, padding=0, dilation=2, pool=None, dtype="f64"),
     "C4": dict(x=(4, 32, 32, 64, 64), w=(64, 32, 3, 3, 3), stride=1, padding=0, dilation=1, pool=(2, 2, 2), dtype="f32"),
 }
+# config 5: small CNN, full Tensor.backward (SURVEY.md §8d concretisation)
+C5 = dict(batch=2048, dtype="f32")
 NP_DTYPE = {"f32": np.float32, "f64": np.float64}
 
 
@@ -451,18 +453,173 @@ def run_ours(args, cfg, name):
         dist.destroy_process_group()
 
 
+def c5_params(dt):
+    r = np.random.default_rng(1)
+    return dict(
+        w1=(r.standard_normal((32, 3, 3, 3)) * 0.1).astype(dt), b1=np.zeros((1, 32, 1, 1), dt),
+        w2=(r.standard_normal((64, 32, 3, 3)) * 0.05).astype(dt), b2=np.zeros((1, 64, 1, 1), dt),
+        wd=(r.standard_normal((4096, 10)) * 0.01).astype(dt), bd=np.zeros((10,), dt))
+
+
+def run_c5(args):
+    """BASELINE.json config 5: 2x(conv_nd 3x3 p1 + bias + relu + max_pool 2) + dense 4096->10 +
+    softmax cross-entropy, batch 2048 per GPU, full Tensor.backward; parameter grads are summed
+    over ranks with one all-reduce per tensor on the communication stream."""
+    import mygrad_b200 as mg
+    from mygrad_b200 import Tensor
+    from mygrad_b200._lib import check, lib
+    from mygrad_b200.dist import DataParallel, scale_for_mean_loss
+    from mygrad_b200.nnet import conv_nd, max_pool, relu, softmax_crossentropy
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dp = DataParallel(rank, world, local).init()
+    dt = np.float32
+    B = C5["batch"]
+    xh = np.random.default_rng(100 + rank).standard_normal((B, 3, 32, 32)).astype(dt)
+    labels = np.random.default_rng(200 + rank).integers(0, 10, B)
+    x_dev = mg.asdevice(xh)
+    params = {k: mg.asdevice(v) for k, v in c5_params(dt).items()}
+
+    def step():
+        p = {k: Tensor(v, copy=False) for k, v in params.items()}
+        x = Tensor(x_dev, copy=False, constant=True)
+        h = max_pool(relu(conv_nd(x, p["w1"], stride=1, padding=1) + p["b1"]), (2, 2), 2)
+        h = max_pool(relu(conv_nd(h, p["w2"], stride=1, padding=1) + p["b2"]), (2, 2), 2)
+        loss = softmax_crossentropy(h.reshape(B, -1) @ p["wd"] + p["bd"], labels)
+        loss.backward()
+        if world > 1:   # the loss averages over the local batch: rescale so the sum is the global mean
+            dp.allreduce([t.grad for t in p.values()], scale=scale_for_mean_loss(B, B * world))
+        return loss, p
+
+    def barrier():
+        mg.synchronize()
+        if dist is not None:
+            dist.barrier()
+        mg.synchronize()
+
+    stream = C.c_void_p(mg.current_stream())
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0, n1 = C.c_uint64(0), C.c_uint64(0)
+    lib.mgb_launch_count(C.byref(n0))
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    check(lib.mgb_event_create(C.byref(e0))); check(lib.mgb_event_create(C.byref(e1)))
+    check(lib.mgb_event_record(e0, stream))
+    for _ in range(args.steps):
+        loss, _ = step()
+    check(lib.mgb_event_record(e1, stream))
+    check(lib.mgb_event_synchronize(e1))
+    ms = C.c_float(0)
+    check(lib.mgb_event_elapsed_ms(e0, e1, C.byref(ms)))
+    barrier()
+    lib.mgb_launch_count(C.byref(n1))
+    clocks = sampler.stop()
+    total_ms = float(ms.value)
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    # end to end: host batch + labels in, loss out, every step
+    px = mg.pinned_empty(xh.shape, dt)
+    px[...] = xh
+    t0 = time.perf_counter()
+    ke = max(3, min(args.steps, 10))
+    for _ in range(ke):
+        x_dev.set_from_host(px, sync=False)
+        loss, _ = step()
+        lv = loss.item()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / ke
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = c5_reference(xh[:256], labels[:256], dt)
+    if rank == 0:
+        line = {
+            "metric": "small CNN (config 5) fwd+bwd samples/sec", "value": world * B / (ms_per_step * 1e-3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5: x=(2048,3,32,32) -> conv3x3(32)+b+relu+pool2 -> conv3x3(64)+b+relu+pool2 -> "
+                                   "dense 4096x10 -> softmax_crossentropy; Tensor.backward; x constant",
+                       "per_gpu_batch": B, "parallelism": f"dp{world}" if world > 1 else "single GPU"},
+            "clocks": clocks, "gpu_launches": int(n1.value - n0.value), "loss": lv,
+            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(px.nbytes + labels.nbytes), "d2h_bytes_per_step": 4},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    barrier()
+    dp.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def c5_reference(x, labels, dt):
+    """the reference (or nothing, if it did not travel) on a 256-sample slice of config 5"""
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "mygrad").exists():
+        return None
+    sys.path.insert(0, str(ref))
+    import mygrad as rm
+    from mygrad.nnet.activations import relu as r_relu
+    from mygrad.nnet.layers import conv_nd as r_conv, max_pool as r_pool
+    from mygrad.nnet.losses import softmax_crossentropy as r_xent
+
+    p = {k: rm.Tensor(v) for k, v in c5_params(dt).items()}
+
+    def step():
+        xt = rm.Tensor(x, constant=True)
+        h = r_pool(r_relu(r_conv(xt, p["w1"], stride=1, padding=1) + p["b1"]), (2, 2), 2)
+        h = r_pool(r_relu(r_conv(h, p["w2"], stride=1, padding=1) + p["b2"]), (2, 2), 2)
+        loss = r_xent(h.reshape(x.shape[0], -1) @ p["wd"] + p["bd"], labels)
+        loss.backward()
+        return float(loss.data)
+
+    step()
+    t0 = time.perf_counter()
+    step()
+    dtm = time.perf_counter() - t0
+    return {"value": x.shape[0] / dtm, "unit": "samples/s", "cores": host_threads(), "kind": "reference",
+            "sample": f"batch {x.shape[0]} of 2048, one timed step after one warm-up"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + ["C5"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload == "C5":
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", 0)) == 0:
+                dtp = np.float32
+                r = np.random.default_rng(100)
+                cpu = c5_reference(r.standard_normal((256, 3, 32, 32)).astype(dtp), r.integers(0, 10, 256), dtp)
+                print(json.dumps({"impl": "reference", "metric": "small CNN (config 5) fwd+bwd samples/sec",
+                                  "value": cpu and cpu["value"], "unit": "samples/s", "n_gpus": args.gpus,
+                                  "cpu_baseline": cpu}), flush=True)
+            return
+        return run_c5(args)
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg, args.workload)
