@@ -210,16 +210,6 @@ def run_graph_cases():
     return 4
 
 
-if __name__ == "__main__":
-    print("reference:", mg.__file__)
-    print("conv cases:", run_conv_cases())
-    print("pool cases:", run_pool_cases())
-    print("layer cases:", run_layer_cases())
-    print("graph cases:", run_graph_cases())
-    for f in sorted(HERE.glob("*.npz")):
-        print(f.name, f.stat().st_size, "bytes")
-
-
 # ---- config-5-like small CNN through the reference (scaled down) -----------
 def run_cnn_case():
     from mygrad.nnet.activations import relu
@@ -251,7 +241,14 @@ def run_cnn_case():
     return 2
 
 
+
+
 if __name__ == "__main__":
+    print("reference:", mg.__file__)
+    print("conv cases:", run_conv_cases())
+    print("pool cases:", run_pool_cases())
+    print("layer cases:", run_layer_cases())
+    print("graph cases:", run_graph_cases())
     print("cnn cases:", run_cnn_case())
-    for f in sorted(HERE.glob("cnn*.npz")):
+    for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")
