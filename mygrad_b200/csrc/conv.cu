@@ -151,6 +151,7 @@ template <> struct Tiles<double> {
   using Mid = Cfg<double, 128, 64, 16, 32, 32, 4>;     // 8 warps
   using Small = Cfg<double, 128, 32, 16, 32, 16, 4>;   // 8 warps
   using WBig = Cfg<double, 128, 128, 16, 64, 32, 4>;
+  using WBig96 = Cfg<double, 128, 96, 16, 64, 24, 4>;   // N = 576 = 6 x 96: no padded MMAs at C2
   using WMid = Cfg<double, 64, 128, 16, 32, 32, 4>;
   using WSmall = Cfg<double, 32, 128, 16, 16, 32, 4>;
 };
@@ -159,6 +160,7 @@ template <> struct Tiles<float> {
   using Mid = Cfg<float, 128, 64, 32, 32, 32, 4>;
   using Small = Cfg<float, 128, 32, 32, 32, 16, 4>;
   using WBig = Cfg<float, 128, 128, 32, 64, 32, 4>;
+  using WBig96 = Cfg<float, 128, 96, 32, 64, 24, 4>;
   using WMid = Cfg<float, 64, 128, 32, 32, 32, 4>;
   using WSmall = Cfg<float, 32, 128, 32, 16, 32, 4>;
 };
@@ -198,14 +200,21 @@ void wgrad_shape(int M, int N, int K, int* tiles, int* splits, int* kps) {
   *tiles = t; *splits = std::max(1, s); *kps = per * C::BK;
 }
 
-// which wgrad tile family: by M (= F)
-inline int wgrad_family(int M) { return M > 64 ? 0 : (M > 32 ? 1 : 2); }
+// which wgrad tile family: by M (= F); family 3 = 128x96 when that pads N less than 128x128
+inline int wgrad_family(int M, int N = 0) {
+  if (M > 64) {
+    long long pad128 = (long long)((N + 127) / 128) * 128, pad96 = (long long)((N + 95) / 96) * 96;
+    return (N > 0 && pad96 < pad128) ? 3 : 0;
+  }
+  return M > 32 ? 1 : 2;
+}
 
 template <typename T>
 void wgrad_plan(int M, int N, int K, int* splits, int* kps) {
   int tiles;
-  switch (wgrad_family(M)) {
+  switch (wgrad_family(M, N)) {
     case 0: wgrad_shape<typename Tiles<T>::WBig>(M, N, K, &tiles, splits, kps); break;
+    case 3: wgrad_shape<typename Tiles<T>::WBig96>(M, N, K, &tiles, splits, kps); break;
     case 1: wgrad_shape<typename Tiles<T>::WMid>(M, N, K, &tiles, splits, kps); break;
     default: wgrad_shape<typename Tiles<T>::WSmall>(M, N, K, &tiles, splits, kps); break;
   }
@@ -923,8 +932,9 @@ int wgrad_t(const Plan& p, const T* dy, const T* x, T* dw, void* ws, size_t ws_b
   wp.gb = geom_x_by_output(p);
   wp.M = M; wp.N = N; wp.K = K; wp.k_per_split = kps;
   int rc;
-  switch (wgrad_family(M)) {
+  switch (wgrad_family(M, N)) {
     case 0: rc = launch_wgrad<T, typename Tiles<T>::WBig>(wp, splits, st); break;
+    case 3: rc = launch_wgrad<T, typename Tiles<T>::WBig96>(wp, splits, st); break;
     case 1: rc = launch_wgrad<T, typename Tiles<T>::WMid>(wp, splits, st); break;
     default: rc = launch_wgrad<T, typename Tiles<T>::WSmall>(wp, splits, st); break;
   }

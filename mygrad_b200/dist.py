@@ -16,6 +16,8 @@ import ctypes as C
 import os
 from typing import Iterable, List, Optional, Sequence, Tuple
 
+import numpy as np
+
 from ._lib import check, lib
 from .device_array import DeviceArray, current_stream
 
@@ -49,6 +51,7 @@ class DataParallel:
         self._comm_stream = None
         self._event = None
         self._ready = False
+        self._buckets: dict = {}
 
     # -- setup ---------------------------------------------------------------------
     def init(self) -> "DataParallel":
@@ -82,6 +85,7 @@ class DataParallel:
             lib.mgb_event_destroy(self._event)
             self._comm_stream = self._event = None
         self._ready = False
+        self._buckets.clear()
 
     # -- sharding --------------------------------------------------------------------
     def shard(self, n: int) -> Tuple[int, int]:
@@ -108,8 +112,49 @@ class DataParallel:
         check(lib.mgb_stream_wait_event(C.c_void_p(current_stream()), self._event))
 
     def allreduce(self, grads: Sequence[DeviceArray], scale: Optional[float] = None) -> None:
-        self.allreduce_async(grads)
-        self.wait()
-        if scale is not None and scale != 1.0:
-            for g in grads:
-                g *= scale
+        """sum all-reduce (then optional scaling) of every buffer.  Parameter gradients are small
+        (C5: 0.26 MB in six tensors), so the cost is per-call latency: buffers of one dtype are
+        packed into a single bucket, reduced with ONE collective and unpacked."""
+        grads = list(grads)
+        if self.world_size == 1:
+            if scale is not None and scale != 1.0:
+                for g in grads:
+                    g *= scale
+            return
+        by_dtype: dict = {}
+        for g in grads:
+            by_dtype.setdefault(g.dtype.str, []).append(g)
+        for group in by_dtype.values():
+            if len(group) == 1:
+                self.allreduce_async(group)
+                self.wait()
+                if scale is not None and scale != 1.0:
+                    group[0] *= scale
+                continue
+            total = sum(g.size for g in group)
+            bucket = self._bucket(total, group[0].dtype)
+            stream = C.c_void_p(current_stream())
+            item = group[0].dtype.itemsize
+            off = 0
+            for g in group:
+                check(lib.mgb_memcpy_d2d(C.c_void_p(bucket.ptr + off * item), C.c_void_p(g.ptr),
+                                         C.c_size_t(g.nbytes), stream))
+                off += g.size
+            flat = DeviceArray((total,), group[0].dtype, _ptr=bucket.ptr, _base=bucket)
+            self.allreduce_async([flat])
+            self.wait()
+            if scale is not None and scale != 1.0:
+                flat *= scale
+            off = 0
+            for g in group:
+                check(lib.mgb_memcpy_d2d(C.c_void_p(g.ptr), C.c_void_p(bucket.ptr + off * item),
+                                         C.c_size_t(g.nbytes), stream))
+                off += g.size
+
+    def _bucket(self, n: int, dtype) -> DeviceArray:
+        key = np.dtype(dtype).str
+        buf = self._buckets.get(key)
+        if buf is None or buf.size < n:
+            buf = DeviceArray((max(n, 1 << 16),), dtype)
+            self._buckets[key] = buf
+        return buf

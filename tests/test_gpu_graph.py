@@ -236,3 +236,73 @@ def test_host_pipeline_matches_single_pass():
         out2, _, _ = pipe.step(px, pw)                          # buffers are re-usable
         np.testing.assert_array_equal(out2, o.numpy())
         pipe.close()
+
+
+@pytest.mark.parametrize("path", ["tma", "cpasync", "mma"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_kernels_do_not_write_outside_their_outputs(path, dt, monkeypatch):
+    """compute-sanitizer is closed on this pool, so out-of-bounds WRITES are caught with guard
+    bands: every output sits between two sentinel regions inside one big allocation."""
+    monkeypatch.setenv("MGB_CONV_F32_PATH", path)
+    GUARD, SENT = 8192, -12345.0
+    rng = np.random.default_rng(12)
+    esz = np.dtype(dt).itemsize
+
+    def guarded(n):
+        big = mg.full((n + 2 * GUARD,), SENT, dt)
+        return big, big.ptr + GUARD * esz
+
+    def check_guard(big, n, what):
+        h = big.get()
+        assert np.all(h[:GUARD] == SENT) and np.all(h[GUARD + n:] == SENT), f"{what}: wrote outside its output"
+        return h[GUARD:GUARD + n]
+
+    for (N, Cc, F, X, W, s_, p_, d_) in [(3, 20, 36, (11, 13), (3, 3), 1, 1, 1), (2, 33, 17, (10, 11), (2, 3), 2, 1, 1),
+                                         (2, 16, 130, (5, 6, 7), (2, 2, 2), 1, 0, 1), (5, 3, 4, (12,), (5,), 1, 2, 2)]:
+        nd = len(X)
+        tup = lambda v: (v,) * nd if isinstance(v, int) else tuple(v)
+        xh = rng.standard_normal((N, Cc, *X)).astype(dt)
+        wh = rng.standard_normal((F, Cc, *W)).astype(dt)
+        G = oc.conv_out_shape(X, W, tup(s_), tup(p_), tup(d_))
+        gh = rng.standard_normal((N, F, *G)).astype(dt)
+        d = ConvDesc()
+        d.dtype, d.nd, d.N, d.C, d.F = (0 if dt == np.float32 else 1), nd, N, Cc, F
+        for i in range(nd):
+            d.X[i], d.W[i], d.stride[i], d.pad[i], d.dil[i] = X[i], W[i], tup(s_)[i], tup(p_)[i], tup(d_)[i]
+        xd, wd, gd = mg.asdevice(xh), mg.asdevice(wh), mg.asdevice(gh)
+        for which, (a, b, want) in enumerate([
+                (xd, wd, oc.conv_fwd(xh, wh, s_, p_, d_)),
+                (gd, wd, oc.conv_dx(gh, xh.shape, wh, s_, p_, d_, dtype=dt)),
+                (gd, xd, oc.conv_dw(gh, xh, wh.shape, s_, p_, d_))]):
+            n = C.c_size_t(0)
+            check(lib.mgb_conv_workspace_bytes(C.byref(d), which, C.byref(n)))
+            ws_big, ws_ptr = guarded((n.value + 1024 + esz - 1) // esz + 64)   # room for the alignment shift
+            ws_ptr = (ws_ptr + 1023) // 1024 * 1024          # workspaces are handed out 1 KB aligned
+            out_big, out_ptr = guarded(want.size)
+            fn = (lib.mgb_conv_fwd, lib.mgb_conv_dgrad, lib.mgb_conv_wgrad)[which]
+            check(fn(C.byref(d), C.c_void_p(a.ptr), C.c_void_p(b.ptr), C.c_void_p(out_ptr), C.c_void_p(ws_ptr), n, None))
+            got = check_guard(out_big, want.size, f"conv[{which}] {path}")
+            assert_close(got.reshape(want.shape), want, dt, err_msg=f"conv[{which}] {path}")
+            h = ws_big.get()
+            assert np.all(h[:GUARD] == SENT) and np.all(h[-GUARD:] == SENT), f"conv[{which}] {path}: workspace overrun"
+    # pooling: vector, pair, generic and gather kernels
+    for (shape, pool, stride) in [((3, 4, 16, 24), (2, 2), 2), ((2, 3, 10, 14), (2, 2), 2), ((2, 5, 9, 11), (3, 2), (2, 3)),
+                                  ((2, 2, 4, 6, 8), (2, 2, 2), 2)]:
+        xh = rng.standard_normal(shape).astype(dt)
+        want = oc.max_pool_fwd(xh, pool, stride)
+        gh = rng.standard_normal(want.shape).astype(dt)
+        pd = PoolDesc()
+        npool = len(pool)
+        st = (stride,) * npool if isinstance(stride, int) else stride
+        pd.dtype, pd.nd, pd.mode = (0 if dt == np.float32 else 1), npool, 0
+        pd.lead = int(np.prod(shape[: len(shape) - npool]))
+        for i in range(npool):
+            pd.X[i], pd.P[i], pd.stride[i] = shape[len(shape) - npool + i], pool[i], st[i]
+        xd, gd = mg.asdevice(xh), mg.asdevice(gh)
+        y_big, y_ptr = guarded(want.size)
+        check(lib.mgb_pool_fwd(C.byref(pd), C.c_void_p(xd.ptr), C.c_void_p(y_ptr), None))
+        np.testing.assert_array_equal(check_guard(y_big, want.size, "pool fwd").reshape(want.shape), want)
+        dx_big, dx_ptr = guarded(xh.size)
+        check(lib.mgb_pool_bwd(C.byref(pd), C.c_void_p(gd.ptr), C.c_void_p(xd.ptr), C.c_void_p(dx_ptr), None))
+        np.testing.assert_array_equal(check_guard(dx_big, xh.size, "pool bwd").reshape(shape),
+                                      oc.max_pool_bwd(gh, xh, pool, stride).astype(dt))
