@@ -151,6 +151,11 @@ int mgb_transpose2d(int dtype, int64_t rows, int64_t cols, const void* src, void
  * logsumexp (src/mygrad/math/_special.py:4-68) */
 int mgb_softmax_xent(int dtype, int64_t n, int64_t c, const void* x, const void* labels, void* loss,
                      void* back, void* stream);
+/* matmul with a small output width m <= 32 (classifier heads), bandwidth-bound:
+ * which 0: out (n,m) = a (n,d) @ b (d,m); 1: out (n,d) = a (n,m) @ b (d,m)^T; 2: out (d,m) = a (n,d)^T @ b (n,m)
+ * — MatMul.__call__ / backward_var (src/mygrad/math/misc/ops.py:91-127) */
+int mgb_matmul_skinny(int dtype, int which, int64_t n, int64_t d, int64_t m, const void* a,
+                      const void* b, void* out, void* stream);
 /* dst[i] = (*scalar) * src[i], scalar on the device — `grad * self.back` (softmax_crossentropy.py:50) */
 int mgb_scale_by(int dtype, size_t n, const void* scalar, const void* src, void* dst, void* stream);
 

@@ -78,6 +78,7 @@ EXPORTS = {
     "mgb_transpose2d": (_i, [_i, C.c_int64, C.c_int64, _vp, _vp, _vp]),
     "mgb_softmax_xent": (_i, [_i, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "mgb_scale_by": (_i, [_i, _sz, _vp, _vp, _vp, _vp]),
+    "mgb_matmul_skinny": (_i, [_i, _i, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
     "mgb_device_count": (_i, [C.POINTER(_i)]),
     "mgb_set_device": (_i, [_i]),
     "mgb_get_device": (_i, [C.POINTER(_i)]),

@@ -313,3 +313,166 @@ extern "C" int mgb_scale_by(int dtype, size_t n, const void* scalar, const void*
   MGB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- skinny matmul: (n, d) @ (d, m) with a small m (classifier heads) -------------------------
+// The conv GEMM tiles (128 x >=32) waste the machine on m = 10: these three kernels are
+// bandwidth-bound instead (A is read once, B stays in L2 / shared memory).
+namespace mgb {
+namespace {
+
+constexpr int kSkinnyMaxM = 32;
+
+// C[n][j] = sum_d A[n][d] * B[d][j]: one warp per row, lanes stride d, B^T staged in smem by chunks
+template <typename T>
+__global__ void __launch_bounds__(256) skinny_fwd_kernel(const T* __restrict__ A, const T* __restrict__ B,
+                                                         T* __restrict__ Cout, long long n, int d, int m,
+                                                         int CH) {
+  extern __shared__ unsigned char smem_raw2[];
+  T* bs = reinterpret_cast<T*>(smem_raw2);          // [chunk][m]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  double acc[kSkinnyMaxM];
+#pragma unroll
+  for (int j = 0; j < kSkinnyMaxM; ++j) acc[j] = 0.0;
+  for (int d0 = 0; d0 < d; d0 += CH) {
+    const int len = min(CH, d - d0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < len * m; i += blockDim.x) bs[i] = B[(long long)d0 * m + i];
+    __syncthreads();
+    if (row < n) {
+      const T* a = A + row * d + d0;
+      for (int k = lane; k < len; k += 32) {
+        const double av = (double)a[k];
+        const T* b = bs + k * m;
+#pragma unroll
+        for (int j = 0; j < kSkinnyMaxM; ++j)
+          if (j < m) acc[j] += av * (double)b[j];
+      }
+    }
+  }
+  if (row < n) {
+#pragma unroll
+    for (int j = 0; j < kSkinnyMaxM; ++j)
+      if (j < m) {
+        double v = acc[j];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) Cout[row * m + j] = (T)v;
+      }
+  }
+}
+
+// dA[n][k] = sum_j G[n][j] * B[k][j]: threads over k (coalesced writes), B row in registers
+template <typename T>
+__global__ void __launch_bounds__(256) skinny_da_kernel(const T* __restrict__ G, const T* __restrict__ B,
+                                                        T* __restrict__ dA, long long n, int d, int m) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  T brow[kSkinnyMaxM];
+#pragma unroll
+  for (int j = 0; j < kSkinnyMaxM; ++j) brow[j] = (k < d && j < m) ? B[(long long)k * m + j] : (T)0;
+  __shared__ T gs[64 * kSkinnyMaxM];
+  const long long r0 = (long long)blockIdx.y * 64;
+  const int rows = (int)min(64LL, n - r0);
+  for (int i = threadIdx.x; i < rows * m; i += blockDim.x) gs[i] = G[r0 * m + i];
+  __syncthreads();
+  if (k >= d) return;
+  for (int r = 0; r < rows; ++r) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < kSkinnyMaxM; ++j)
+      if (j < m) acc += (double)gs[r * m + j] * (double)brow[j];
+    dA[(r0 + r) * d + k] = (T)acc;
+  }
+}
+
+// dB[k][j] = sum_n A[n][k] * G[n][j]: threads over k, split over n with float64 partials
+template <typename T>
+__global__ void __launch_bounds__(256) skinny_db_kernel(const T* __restrict__ A, const T* __restrict__ G,
+                                                        double* __restrict__ partial, long long n, int d, int m,
+                                                        long long rows_per_split) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(n, r0 + rows_per_split);
+  __shared__ T gs[64 * kSkinnyMaxM];
+  double acc[kSkinnyMaxM];
+#pragma unroll
+  for (int j = 0; j < kSkinnyMaxM; ++j) acc[j] = 0.0;
+  for (long long rb = r0; rb < r1; rb += 64) {
+    const int rows = (int)min(64LL, r1 - rb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * m; i += blockDim.x) gs[i] = G[rb * m + i];
+    __syncthreads();
+    if (k < d)
+      for (int r = 0; r < rows; ++r) {
+        const double av = (double)A[(rb + r) * d + k];
+#pragma unroll
+        for (int j = 0; j < kSkinnyMaxM; ++j)
+          if (j < m) acc[j] += av * (double)gs[r * m + j];
+      }
+  }
+  if (k < d) {
+    double* out = partial + ((long long)blockIdx.y * d + k) * m;
+#pragma unroll
+    for (int j = 0; j < kSkinnyMaxM; ++j)
+      if (j < m) out[j] = acc[j];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) skinny_db_finish(const double* __restrict__ partial, T* __restrict__ dB,
+                                                        long long total, int splits) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int s = 0; s < splits; ++s) acc += partial[(long long)s * total + i];   // fixed order
+    dB[i] = (T)acc;
+  }
+}
+
+template <typename T>
+int skinny_t(int which, long long n, int d, int m, const T* a, const T* b, T* out, cudaStream_t st) {
+  if (which == 0) {
+    int ch = std::max(32, std::min(1024, (int)(40960 / (m * sizeof(T))) / 32 * 32));   // <= 40 KB of smem
+    size_t smem = (size_t)ch * m * sizeof(T);
+    skinny_fwd_kernel<T><<<(unsigned)((n + 7) / 8), 256, smem, st>>>(a, b, out, n, d, m, ch);
+    MGB_LAUNCH_CHECK();
+  } else if (which == 1) {
+    dim3 grid((d + 255) / 256, (unsigned)((n + 63) / 64));
+    skinny_da_kernel<T><<<grid, 256, 0, st>>>(a, b, out, n, d, m);
+    MGB_LAUNCH_CHECK();
+  } else {
+    int kb = (d + 255) / 256;
+    int splits = (int)std::max<long long>(1, std::min<long long>((n + 63) / 64, (4LL * sm_count() + kb - 1) / kb));
+    long long per = ((n + splits - 1) / splits + 63) / 64 * 64;
+    splits = (int)((n + per - 1) / per);
+    double* partial = nullptr;
+    MGB_CUDA(cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)splits * d * m, st));
+    skinny_db_kernel<T><<<dim3(kb, splits), 256, 0, st>>>(a, b, partial, n, d, m, per);
+    MGB_LAUNCH_CHECK();
+    long long total = (long long)d * m;
+    skinny_db_finish<T><<<(unsigned)std::min<long long>((total + 255) / 256, 1024), 256, 0, st>>>(partial, out, total, splits);
+    MGB_LAUNCH_CHECK();
+    MGB_CUDA(cudaFreeAsync(partial, st));
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace mgb
+
+// which = 0: out (n,m) = a (n,d) @ b (d,m);  1: out (n,d) = a=G (n,m) @ b (d,m)^T;
+//         2: out (d,m) = a (n,d)^T @ b=G (n,m).   Requires m <= 32.
+extern "C" int mgb_matmul_skinny(int dtype, int which, int64_t n, int64_t d, int64_t m, const void* a,
+                                 const void* b, void* out, void* stream) {
+  if (dtype != MGB_F32 && dtype != MGB_F64) return fail("mgb_matmul_skinny: bad dtype %d", dtype);
+  if (which < 0 || which > 2) return fail("mgb_matmul_skinny: which=%d", which);
+  if (m < 1 || m > kSkinnyMaxM || n < 0 || d < 0 || d > INT32_MAX) return fail("mgb_matmul_skinny: needs 1 <= m <= %d", kSkinnyMaxM);
+  if (n == 0 || d == 0) {
+    size_t esz = dtype == MGB_F32 ? 4 : 8;
+    size_t cnt = which == 0 ? (size_t)(n * m) : (which == 1 ? (size_t)(n * d) : (size_t)(d * m));
+    if (cnt) MGB_CUDA(cudaMemsetAsync(out, 0, cnt * esz, as_stream(stream)));
+    return 0;
+  }
+  if (!a || !b || !out) return fail("mgb_matmul_skinny: null");
+  if (dtype == MGB_F32)
+    return skinny_t<float>(which, n, (int)d, (int)m, (const float*)a, (const float*)b, (float*)out, as_stream(stream));
+  return skinny_t<double>(which, n, (int)d, (int)m, (const double*)a, (const double*)b, (double*)out, as_stream(stream));
+}

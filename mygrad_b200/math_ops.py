@@ -72,6 +72,14 @@ class MatMul(Operation):
         self._dtype = np.result_type(x.dtype, y.dtype)
         n, d = x.shape
         m = y.shape[1]
+        self._skinny = m <= 32
+        if self._skinny:   # classifier-head shape: bandwidth-bound kernels instead of GEMM tiles
+            self._a = x.astype(self._dtype, copy=False)
+            self._b = y.astype(self._dtype, copy=False)
+            out = DeviceArray((n, m), self._dtype)
+            check(lib.mgb_matmul_skinny(out.code, 0, n, d, m, C.c_void_p(self._a.ptr), C.c_void_p(self._b.ptr),
+                                        C.c_void_p(out.ptr), C.c_void_p(current_stream())))
+            return out
         desc = self._desc = ConvDesc()
         desc.dtype, desc.nd = (0 if self._dtype == np.float32 else 1), 1
         desc.N, desc.C, desc.F = n, d, m
@@ -102,6 +110,14 @@ class MatMul(Operation):
         a, b = (v.data for v in self.variables)
         g = grad.astype(self._dtype, copy=False)
         stream = C.c_void_p(current_stream())
+        if self._skinny:
+            n, d = a.shape
+            m = b.shape[1]
+            out = DeviceArray(a.shape if index == 0 else b.shape, self._dtype)
+            lhs, rhs = (g, self._b) if index == 0 else (self._a, g)
+            check(lib.mgb_matmul_skinny(out.code, 1 if index == 0 else 2, n, d, m, C.c_void_p(lhs.ptr),
+                                        C.c_void_p(rhs.ptr), C.c_void_p(out.ptr), stream))
+            return out
         if index == 0:      # dA = grad @ B^T  == conv dX
             da = DeviceArray(a.shape, self._dtype)
             ws, nbytes = self._ws(1)
