@@ -514,11 +514,16 @@ int tma_launch(const TmaJob& j, cudaStream_t st) {
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return 2;
   }
+  // CTA pairs (tcgen05 cta_group::2, conv_tma2_kernel) are opt-in: MGB_CONV_2CTA=1.  Measured at C2
+  // (N tile 128): 0.82 ms vs 0.52 ms for the single-CTA kernel — the UMMA stream itself runs slower
+  // (the issuing thread never waits for data), so halving the B bytes per SM does not pay at this N.
+  const char* e2 = getenv("MGB_CONV_2CTA");
+  const bool pair = (e2 && e2[0] == '1') && j.bn >= 32 && j.bn % 32 == 0;
   {
     long long K = (long long)j.ntaps * j.cpad;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)j.rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    cuuint32_t box[2] = {32u, (cuuint32_t)j.bn};
+    cuuint32_t box[2] = {32u, (cuuint32_t)(pair ? j.bn / 2 : j.bn)};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r1 = enc(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)j.b_hi, dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -540,6 +545,19 @@ int tma_launch(const TmaJob& j, cudaStream_t st) {
   if (total > INT32_MAX) return 2;
   tp.Nbatch = (int)j.nbatch; tp.Nout = j.nout; tp.nchunk = j.cpad / 32; tp.ntaps = j.ntaps;
   tp.bn = j.bn; tp.ny = j.ny; tp.tmem_cols = pow2_cols(2 * j.bn); tp.total_tiles = (int)total;
+  if (pair) {
+    constexpr int STAGES = 4;
+    const int pix_tiles = (int)(total / j.ny);
+    const long long pairs = (long long)((pix_tiles + 1) / 2) * j.ny;
+    tp.total_tiles = (int)pairs;
+    size_t smem = tma::smem_bytes(j.bn / 2, STAGES);
+    MGB_CUDA(cudaFuncSetAttribute(tma::conv_tma2_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    int grid = (int)std::min<long long>(2 * pairs, sm_count() / 2 * 2);
+    tma::conv_tma2_kernel<STAGES><<<grid, tma::THREADS, smem, st>>>(tp, ma_hi, ma_lo, mb_hi, mb_lo, pix_tiles);
+    MGB_LAUNCH_CHECK();
+    return 0;
+  }
   constexpr int STAGES = 3;
   size_t smem = tma::smem_bytes(j.bn, STAGES);
   MGB_CUDA(cudaFuncSetAttribute(tma::conv_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -229,6 +229,242 @@ conv_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUt
   if (warp == 1) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ---- the same GEMM on a CTA pair: tcgen05 cta_group::2 ------------------------------------------
+//
+// Two CTAs of one cluster (same TPC) run ONE UMMA of M = 256: CTA r owns pixel box 2q+r (its
+// own A tile and 128 TMEM lanes) and HALF of the filter tile (rows r*bn/2 ...), so every SM
+// reads only half of B from its shared memory per MMA and TMA writes half of B per stage —
+// the kernel above is bound by exactly that shared-memory traffic.  The leader CTA (rank 0)
+// issues the MMAs; both CTAs' TMA transactions complete on the leader's full barrier;
+// tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs.
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// address of `local` (a shared::cta address of this CTA) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0,
+                                             int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0,
+                                             int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same offset in BOTH CTAs once the MMAs issued so far retire
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+          tc::smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem2_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tc::smem_u32(slot)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem2_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// params: as TmaParams; total_tiles counts PAIR tiles (two pixel boxes x one channel tile),
+// pix_tiles = number of real pixel boxes
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+conv_tma2_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUtensorMap map_a_hi,
+                 const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_b_hi,
+                 const __grid_constant__ CUtensorMap map_b_lo, int pix_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int half_n = p.bn / 2;
+  const int b_tile_bytes = half_n * 128;                 // this CTA's half of the filter tile
+  const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int S = p.ntaps * p.nchunk;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_b_hi); prefetch_tmap(&map_b_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(full_bar + s, 2);      // leader's expect_tx arrive + the peer's arrive
+      tc::mbar_init(empty_bar + s, 1);     // multicast commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tfull_bar + b, 1);     // multicast commit
+      tc::mbar_init(tempty_bar + b, 256);  // epilogue threads of both CTAs (leader's copy is the one waited on)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) tmem2_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // barriers of both CTAs are initialised before any remote signal
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = tc::smem_u32(smem);
+
+  // pair tile -> (channel tile y, pixel-box pair q); this CTA's pixel box = 2q + rank
+  auto my_box = [&](int pair, TileCoord* tcd, bool* real) {
+    const int y = pair % p.ny, q = pair / p.ny;
+    const int box = 2 * q + (int)rank;
+    *real = box < pix_tiles;
+    int t = *real ? box : 0;
+    tcd->y = y;
+    tcd->t2 = t % p.tiles[2]; t /= p.tiles[2];
+    tcd->t1 = t % p.tiles[1]; t /= p.tiles[1];
+    tcd->t0 = t % p.tiles[0]; t /= p.tiles[0];
+    tcd->n0 = *real ? t * p.boxn : p.Nbatch;      // a padding box reads past the batch: all zeros
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own A box, own half of B; completion on the LEADER's barrier =====
+      int it = 0;
+      for (int pair = cluster_id; pair < p.total_tiles; pair += nclusters) {
+        TileCoord tcd;
+        bool real;
+        my_box(pair, &tcd, &real);
+        const int x0 = tcd.t0 * p.box[0] * p.pmul[0] + p.base[0];
+        const int x1 = tcd.t1 * p.box[1] * p.pmul[1] + p.base[1];
+        const int x2 = tcd.t2 * p.box[2] * p.pmul[2] + p.base[2];
+        for (int s = 0; s < S; ++s, ++it) {
+          const int stage = it % STAGES;
+          if (it >= STAGES) tc::mbar_wait(empty_bar + stage, (uint32_t)((it / STAGES - 1) & 1));
+          const int tap = s / p.nchunk, cc = s - tap * p.nchunk;
+          const int4 tv = __ldg(reinterpret_cast<const int4*>(p.taps) + tap);
+          const uint32_t a_hi = smem_base + stage * stage_bytes;
+          const uint32_t bar = map_to_cta(tc::smem_u32(full_bar + stage), 0);
+          if (rank == 0) mbar_expect_tx(full_bar + stage, (uint32_t)(2 * stage_bytes));
+          else mbar_arrive_cluster(bar);
+          tma2_load_5d(a_hi, &map_a_hi, bar, cc * BK, x2 + tv.w, x1 + tv.z, x0 + tv.y, tcd.n0);
+          tma2_load_5d(a_hi + A_TILE_BYTES, &map_a_lo, bar, cc * BK, x2 + tv.w, x1 + tv.z, x0 + tv.y, tcd.n0);
+          tma2_load_2d(a_hi + 2 * A_TILE_BYTES, &map_b_hi, bar, s * BK, tcd.y * p.bn + (int)rank * half_n);
+          tma2_load_2d(a_hi + 2 * A_TILE_BYTES + b_tile_bytes, &map_b_lo, bar, s * BK,
+                       tcd.y * p.bn + (int)rank * half_n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer: leader CTA only, M = 256 over the pair =====
+      const uint32_t idesc = (tc::idesc_tf32(p.bn) & ~(0x1Fu << 24)) | ((256u >> 4) << 24);
+      int it = 0, local = 0;
+      for (int pair = cluster_id; pair < p.total_tiles; pair += nclusters, ++local) {
+        const int buf = local & 1;
+        if (local >= 2) tc::mbar_wait(tempty_bar + buf, (uint32_t)((local / 2 - 1) & 1));
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.bn);
+        for (int s = 0; s < S; ++s, ++it) {
+          const int stage = it % STAGES;
+          tc::mbar_wait(full_bar + stage, (uint32_t)((it / STAGES) & 1));
+          tc::tc_fence_after();
+          const uint32_t a_hi = smem_base + stage * stage_bytes;
+          const uint32_t a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = a_lo + A_TILE_BYTES;
+          const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint64_t dah = tc::smem_desc_k_sw128(a_hi + j * 32), dal = tc::smem_desc_k_sw128(a_lo + j * 32);
+            const uint64_t dbh = tc::smem_desc_k_sw128(b_hi + j * 32), dbl = tc::smem_desc_k_sw128(b_lo + j * 32);
+            umma2_tf32(tmem_d, dal, dbh, idesc, (s | j) ? 1u : 0u);
+            umma2_tf32(tmem_d, dah, dbl, idesc, 1u);
+            umma2_tf32(tmem_d, dah, dbh, idesc, 1u);
+          }
+          umma2_commit(empty_bar + stage);
+        }
+        umma2_commit(tfull_bar + buf);
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): own 128 TMEM lanes =====
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int i2 = r % p.box[2];
+    const int r1 = r / p.box[2];
+    const int i1 = r1 % p.box[1];
+    const int r0 = r1 / p.box[1];
+    const int i0 = r0 % p.box[0];
+    const int in = r0 / p.box[0];
+    int local = 0;
+    for (int pair = cluster_id; pair < p.total_tiles; pair += nclusters, ++local) {
+      const int buf = local & 1;
+      TileCoord tcd;
+      bool real;
+      my_box(pair, &tcd, &real);
+      const int n = tcd.n0 + in;
+      const int g0 = tcd.t0 * p.box[0] + i0, g1 = tcd.t1 * p.box[1] + i1, g2 = tcd.t2 * p.box[2] + i2;
+      const bool pv = real && n < p.Nbatch && g0 < p.P[0] && g1 < p.P[1] && g2 < p.P[2];
+      long long rowoff = -1;
+      if (pv)
+        rowoff = (long long)n * p.om.sample_stride +
+                 (long long)(g0 * p.om.omul[0] + p.om.obase[0]) * p.om.os[0] +
+                 (long long)(g1 * p.om.omul[1] + p.om.obase[1]) * p.om.os[1] +
+                 (long long)(g2 * p.om.omul[2] + p.om.obase[2]) * p.om.os[2];
+      tc::mbar_wait(tfull_bar + buf, (uint32_t)((local / 2) & 1));
+      tc::tc_fence_after();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.bn);
+      const int ch0 = tcd.y * p.bn;
+      for (int col = 0; col < p.bn; col += 16) {
+        uint32_t v[16];
+        tc::tmem_ld16(lane_base + (uint32_t)col, v);
+        if (rowoff >= 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            int ch = ch0 + col + j;
+            if (ch < p.Nout) p.out[rowoff + (long long)ch * p.om.chan_stride] = __uint_as_float(v[j]);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      mbar_arrive_cluster(map_to_cta(tc::smem_u32(tempty_bar + buf), 0));   // the leader waits for all 256
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // nobody frees TMEM / exits while the pair still uses it
+  if (warp == 1) tmem2_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 // ---- wgrad with TMA-staged MN-major operands -------------------------------------------------
 //
 // K = output pixels, walked box by box (b2 x b1 x b0 x bn = 16 pixels per stage); for each
