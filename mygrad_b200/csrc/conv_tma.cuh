@@ -95,7 +95,8 @@ conv_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_tile_bytes = p.bn * 128;
-  const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+  constexpr int a_tile_bytes = A_TILE_BYTES;
+  const int stage_bytes = 2 * a_tile_bytes + 2 * b_tile_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;    // accumulator buffer ready for the epilogue
@@ -140,11 +141,12 @@ conv_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUt
           const int4 tv = __ldg(reinterpret_cast<const int4*>(p.taps) + tap);
           const uint32_t a_hi = smem_base + stage * stage_bytes;
           mbar_expect_tx(full_bar + stage, (uint32_t)stage_bytes);
-          tma_load_5d(a_hi, &map_a_hi, full_bar + stage, cc * BK, x2 + tv.w, x1 + tv.z, x0 + tv.y, tcd.n0);
-          tma_load_5d(a_hi + A_TILE_BYTES, &map_a_lo, full_bar + stage, cc * BK, x2 + tv.w, x1 + tv.z,
+          const int xs = x2 + tv.w;
+          tma_load_5d(a_hi, &map_a_hi, full_bar + stage, cc * BK, xs, x1 + tv.z, x0 + tv.y, tcd.n0);
+          tma_load_5d(a_hi + a_tile_bytes, &map_a_lo, full_bar + stage, cc * BK, xs, x1 + tv.z,
                       x0 + tv.y, tcd.n0);
-          tma_load_2d(a_hi + 2 * A_TILE_BYTES, &map_b_hi, full_bar + stage, s * BK, tcd.y * p.bn);
-          tma_load_2d(a_hi + 2 * A_TILE_BYTES + b_tile_bytes, &map_b_lo, full_bar + stage, s * BK,
+          tma_load_2d(a_hi + 2 * a_tile_bytes, &map_b_hi, full_bar + stage, s * BK, tcd.y * p.bn);
+          tma_load_2d(a_hi + 2 * a_tile_bytes + b_tile_bytes, &map_b_lo, full_bar + stage, s * BK,
                       tcd.y * p.bn);
         }
       }
@@ -164,8 +166,8 @@ conv_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUt
           tc::mbar_wait(full_bar + stage, (uint32_t)((it / STAGES) & 1));
           tc::tc_fence_after();
           const uint32_t a_hi = smem_base + stage * stage_bytes;
-          const uint32_t a_lo = a_hi + A_TILE_BYTES;
-          const uint32_t b_hi = a_lo + A_TILE_BYTES;
+          const uint32_t a_lo = a_hi + a_tile_bytes;
+          const uint32_t b_hi = a_lo + a_tile_bytes;
           const uint32_t b_lo = b_hi + b_tile_bytes;
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
