@@ -430,6 +430,10 @@ def run_ours(args, cfg, name):
             achieved = ph["bytes"] / (ph["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": None, "peak_basis": peak_src}
+        # DRAM traffic of the dominant kernel from the committed ncu capture (null when none was taken)
+        tfile = ROOT / "profiles" / "r01_traffic.json"
+        if tfile.exists():
+            roof["traffic"] = json.loads(tfile.read_text()).get(args.workload, {}).get(top)
         for k, v in phases.items():
             if "flops" in v:
                 v["tflops"] = v["flops"] / (v["ms"] * 1e-3) / 1e12
