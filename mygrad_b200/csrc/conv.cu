@@ -459,7 +459,9 @@ inline int next_pow2(long long v) { int r = 1; while (r < v) r <<= 1; return r; 
 
 // pixel box (powers of two, 128 pixels) with the fewest tiles; false when no box fits TMA's limits
 bool choose_box(const int P[3], const int pmul[3], long long nbatch, int box[3], int* boxn,
-                int pixels = 128) {
+                int pixels = 128, bool merged_outer = false) {
+  // merged_outer: the batch and axis 0 are one TMA dimension: boxes must tile axis 0 exactly and
+  // may not span samples
   long long best = -1;
   for (int b0 = 1; b0 <= pixels; b0 <<= 1)
     for (int b1 = 1; b0 * b1 <= pixels; b1 <<= 1)
@@ -467,6 +469,7 @@ bool choose_box(const int P[3], const int pmul[3], long long nbatch, int box[3],
         int bn = pixels / (b0 * b1 * b2);
         if (b0 > next_pow2(P[0]) || b1 > next_pow2(P[1]) || b2 > next_pow2(P[2]) || bn > next_pow2(nbatch)) continue;
         if (b0 * pmul[0] > 256 || b1 * pmul[1] > 256 || b2 * pmul[2] > 256 || bn > 256) continue;
+        if (merged_outer && (bn != 1 || P[0] % b0 != 0)) continue;
         long long tiles = ((P[0] + b0 - 1) / b0) * (long long)((P[1] + b1 - 1) / b1) * ((P[2] + b2 - 1) / b2) *
                           ((nbatch + bn - 1) / bn);
         // fewer tiles first; then wider contiguous runs for the epilogue stores
@@ -739,21 +742,29 @@ int wgrad_tma_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const fl
   if (!enc || !tma_enabled()) return 2;
   for (int i = 0; i < 3; ++i) if (p.X[i] < 1 || p.G[i] < 1) return 2;
   tma::WgradTmaParams wp;
-  // blocked maps need the channel-block axis as a fifth dimension: <= 2 spatial dims, and the
-  // CTA's (tap, c-block) ranges must be whole taps
-  wp.blocked = (p.X[0] == 1 && p.G[0] == 1 && L.nbpc % L.cblocks == 0) ? 1 : 0;
+  // blocked maps need the channel-block axis as a fifth dimension, so batch and axis 0 share one
+  // (trivially with <= 2 spatial dims; otherwise axis 0 must be unpadded and tiled exactly by the
+  // boxes), and the CTA's (tap, c-block) ranges must be whole taps
+  const bool flat = p.X[0] == 1 && p.G[0] == 1;              // <= 2 spatial dims
+  const bool mergeable = !flat && p.Pd[0] == 0;               // 3-D with an unpadded outer axis
+  wp.blocked = ((flat || mergeable) && L.nbpc % L.cblocks == 0) ? 1 : 0;
   wp.pix = wp.blocked ? 32 : tma::WG_PIX;
-  if (!choose_box(p.G, p.S, p.N, wp.box, &wp.boxn, wp.pix)) return 2;
+  if (wp.blocked && !flat) {
+    if (!choose_box(p.G, p.S, p.N, wp.box, &wp.boxn, wp.pix, true)) { wp.blocked = 0; wp.pix = tma::WG_PIX; }
+  }
+  if ((!wp.blocked || flat) && !choose_box(p.G, p.S, p.N, wp.box, &wp.boxn, wp.pix)) return 2;
+  wp.X0 = p.X[0]; wp.G0 = p.G[0];
   CUtensorMap mdy_hi, mdy_lo, mx_hi, mx_lo;
   auto encode = [&](CUtensorMap* m, const float* base, int cpad, const int X[3], const int mul[3], int nblk) {
     cuuint64_t dims[5], strides[4];
     cuuint32_t box[5], estr[5];
-    if (wp.blocked) {   // (32, X2, X1, N, cpad/32)
-      dims[0] = 32; dims[1] = X[2]; dims[2] = X[1]; dims[3] = p.N; dims[4] = cpad / 32;
+    if (wp.blocked) {   // (32, X2, X1, N*X0, cpad/32)
+      dims[0] = 32; dims[1] = X[2]; dims[2] = X[1]; dims[3] = (cuuint64_t)p.N * X[0]; dims[4] = cpad / 32;
       strides[0] = (cuuint64_t)cpad * 4; strides[1] = strides[0] * X[2]; strides[2] = strides[1] * X[1];
       strides[3] = 128;
-      box[0] = 32; box[1] = wp.box[2] * mul[2]; box[2] = wp.box[1] * mul[1]; box[3] = wp.boxn; box[4] = nblk;
-      estr[0] = 1; estr[1] = mul[2]; estr[2] = mul[1]; estr[3] = 1; estr[4] = 1;
+      box[0] = 32; box[1] = wp.box[2] * mul[2]; box[2] = wp.box[1] * mul[1];
+      box[3] = flat ? wp.boxn : wp.box[0] * mul[0]; box[4] = nblk;
+      estr[0] = 1; estr[1] = mul[2]; estr[2] = mul[1]; estr[3] = flat ? 1 : mul[0]; estr[4] = 1;
     } else {            // (cpad, X2, X1, X0, N)
       dims[0] = cpad; dims[1] = X[2]; dims[2] = X[1]; dims[3] = X[0]; dims[4] = p.N;
       strides[0] = (cuuint64_t)cpad * 4; strides[1] = strides[0] * X[2]; strides[2] = strides[1] * X[1];

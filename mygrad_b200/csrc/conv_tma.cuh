@@ -486,11 +486,14 @@ struct WgradTmaParams {
   int boxes_total, boxes_per_split;
   int tmem_cols;
   int pix;                                 // pixels per stage: 16 or 32
-  // "blocked" tensor maps (<= 2 spatial dims): the channel axis is split into (32, block) and
+  // "blocked" tensor maps: the batch and the outermost spatial axis are merged into one
+  // dimension (u = n*X0 + x0: legal when that axis is unpadded and the boxes tile it exactly, and
+  // trivially when X0 = 1), the channel axis is split into (32, block) and
   // the block index is the slowest box dimension, so ONE TMA brings several 32-channel
   // blocks ([block][pixel][128 B], exactly the UMMA operand order): 4 f-blocks of dy, and
   // all c-blocks of one tap of x.  Small boxes are what limits TMA here, not bytes.
   int blocked;
+  int X0, G0;                              // outermost spatial extents of x and dy (for the merged axis)
 };
 
 inline size_t wgrad_smem_bytes(int nbpc, int stages, int pix) {
@@ -555,15 +558,17 @@ wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant
         const uint32_t b_hi = a_hi + 2 * a_plane;
         const int x0 = g0 * p.S[0] - p.Pd[0], x1 = g1 * p.S[1] - p.Pd[1], x2 = g2 * p.S[2] - p.Pd[2];
         if (p.blocked) {
-          // coordinates (ch-in-block, x2, x1, n, block)
-          tma_load_5d(a_hi, &map_dy_hi, full_bar + stage, 0, g2, g1, n0, m0 / 32);
-          tma_load_5d(a_hi + a_plane, &map_dy_lo, full_bar + stage, 0, g2, g1, n0, m0 / 32);
+          // coordinates (ch-in-block, x2, x1, u = n*X0 + x0, block)
+          const int uy = n0 * p.G0 + g0, ux = n0 * p.X0 + x0;
+          tma_load_5d(a_hi, &map_dy_hi, full_bar + stage, 0, g2, g1, uy, m0 / 32);
+          tma_load_5d(a_hi + a_plane, &map_dy_lo, full_bar + stage, 0, g2, g1, uy, m0 / 32);
           for (int b = 0; b < nvalid; b += p.cblocks) {
             const int tap = (blk0 + b) / p.cblocks;
             const int4 tv = __ldg(reinterpret_cast<const int4*>(p.taps) + tap);
-            tma_load_5d(b_hi + b * WG_BLK_BYTES, &map_x_hi, full_bar + stage, 0, x2 + tv.w, x1 + tv.z, n0, 0);
+            tma_load_5d(b_hi + b * WG_BLK_BYTES, &map_x_hi, full_bar + stage, 0, x2 + tv.w, x1 + tv.z,
+                        ux + tv.y, 0);
             tma_load_5d(b_hi + b_plane + b * WG_BLK_BYTES, &map_x_lo, full_bar + stage, 0, x2 + tv.w,
-                        x1 + tv.z, n0, 0);
+                        x1 + tv.z, ux + tv.y, 0);
           }
         } else {
           for (int mb = 0; mb < 4; ++mb) {

@@ -210,6 +210,9 @@ TC_CASES = [
     (2, 32, 64, (6, 7, 8), (3, 3, 3), 1, 1, 1),
     (2, 16, 16, (5, 9, 9), (2, 3, 3), (1, 2, 2), 0, 1),
     (5, 32, 32, (30, 30), (3, 3), 1, 1, 1),
+    # 3-D with an unpadded outer axis: wgrad merges (batch, axis 0) into one TMA dimension
+    (3, 32, 32, (7, 8, 8), (3, 3, 3), (2, 1, 1), (0, 1, 1), 1),
+    (2, 32, 48, (10, 6, 6), (2, 3, 3), (2, 1, 1), (0, 1, 0), (3, 1, 1)),
 ]
 
 
