@@ -547,7 +547,12 @@ int tma_launch(const TmaJob& j, cudaStream_t st) {
   total *= tp.tiles_n;
   if (total > INT32_MAX) return 2;
   tp.Nbatch = (int)j.nbatch; tp.Nout = j.nout; tp.nchunk = j.cpad / 32; tp.ntaps = j.ntaps;
-  tp.bn = j.bn; tp.ny = j.ny; tp.tmem_cols = pow2_cols(2 * j.bn); tp.total_tiles = (int)total;
+  tp.bn = j.bn; tp.ny = j.ny; tp.total_tiles = (int)total;
+  // N-concatenated B operand (see TmaParams::ncat): default on, MGB_CONV_NCAT=0 restores three UMMAs
+  const char* e3 = getenv("MGB_CONV_NCAT");
+  tp.ncat = (!pair && !(e3 && e3[0] == '0') && j.bn % 8 == 0 && 2 * j.bn <= 256) ? 1 : 0;
+  tp.acc_cols = tp.ncat ? 2 * j.bn : j.bn;
+  tp.tmem_cols = pow2_cols(2 * tp.acc_cols);
   if (pair) {
     constexpr int STAGES = 4;
     const int pix_tiles = (int)(total / j.ny);

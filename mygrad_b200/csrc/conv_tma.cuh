@@ -40,6 +40,12 @@ struct TmaParams {
   int bn, ny;                           // channel tile, number of channel tiles
   int tmem_cols;
   int total_tiles;                      // tiles_n*tiles[0]*tiles[1]*tiles[2]*ny
+  // ncat = 1: the B_hi and B_lo tiles (adjacent in the stage, same K-major layout) are read as ONE
+  // operand of 2*bn rows, so a_hi*[b_hi | b_lo] is a single UMMA of N = 2*bn into accumulator columns
+  // [0, 2bn) and a_lo*b_hi a second one into [0, bn): two UMMAs and (A + 2B) + (A + B) bytes of
+  // shared-memory reads per k-step instead of three UMMAs and 3(A + B).  The epilogue adds the halves.
+  int ncat;
+  int acc_cols;                         // accumulator columns per buffer: bn or 2*bn
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -155,12 +161,13 @@ conv_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUt
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = tc::idesc_tf32(p.bn);
+      const uint32_t idesc2 = tc::idesc_tf32(2 * p.bn);   // a_hi x [b_hi | b_lo]
       int it = 0, local = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
         const int buf = local & 1;
         if (local >= 2) tc::mbar_wait(tempty_bar + buf, (uint32_t)((local / 2 - 1) & 1));
         tc::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.bn);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.acc_cols);
         for (int s = 0; s < S; ++s, ++it) {
           const int stage = it % STAGES;
           tc::mbar_wait(full_bar + stage, (uint32_t)((it / STAGES) & 1));
@@ -169,13 +176,23 @@ conv_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUt
           const uint32_t a_lo = a_hi + a_tile_bytes;
           const uint32_t b_hi = a_lo + a_tile_bytes;
           const uint32_t b_lo = b_hi + b_tile_bytes;
+          if (p.ncat) {
 #pragma unroll
-          for (int j = 0; j < BK / 8; ++j) {
-            const uint64_t dah = tc::smem_desc_k_sw128(a_hi + j * 32), dal = tc::smem_desc_k_sw128(a_lo + j * 32);
-            const uint64_t dbh = tc::smem_desc_k_sw128(b_hi + j * 32), dbl = tc::smem_desc_k_sw128(b_lo + j * 32);
-            tc::umma_tf32(tmem_d, dal, dbh, idesc, (s | j) ? 1u : 0u);
-            tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-            tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            for (int j = 0; j < BK / 8; ++j) {
+              const uint64_t dah = tc::smem_desc_k_sw128(a_hi + j * 32), dal = tc::smem_desc_k_sw128(a_lo + j * 32);
+              const uint64_t dbh = tc::smem_desc_k_sw128(b_hi + j * 32);
+              tc::umma_tf32(tmem_d, dah, dbh, idesc2, (s | j) ? 1u : 0u);   // cols [0,bn) hi*hi, [bn,2bn) hi*lo
+              tc::umma_tf32(tmem_d, dal, dbh, idesc, 1u);                   // cols [0,bn) += lo*hi
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < BK / 8; ++j) {
+              const uint64_t dah = tc::smem_desc_k_sw128(a_hi + j * 32), dal = tc::smem_desc_k_sw128(a_lo + j * 32);
+              const uint64_t dbh = tc::smem_desc_k_sw128(b_hi + j * 32), dbl = tc::smem_desc_k_sw128(b_lo + j * 32);
+              tc::umma_tf32(tmem_d, dal, dbh, idesc, (s | j) ? 1u : 0u);
+              tc::umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+              tc::umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            }
           }
           tc::umma_commit(empty_bar + stage);
         }
@@ -208,11 +225,17 @@ conv_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUt
                  (long long)(g2 * p.om.omul[2] + p.om.obase[2]) * p.om.os[2];
       tc::mbar_wait(tfull_bar + buf, (uint32_t)((local / 2) & 1));
       tc::tc_fence_after();
-      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.bn);
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.acc_cols);
       const int ch0 = tcd.y * p.bn;
       for (int col = 0; col < p.bn; col += 16) {
         uint32_t v[16];
         tc::tmem_ld16(lane_base + (uint32_t)col, v);
+        if (p.ncat) {
+          uint32_t u[16];
+          tc::tmem_ld16(lane_base + (uint32_t)(p.bn + col), u);   // the a_hi*b_lo half
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
         if (rowoff >= 0) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
