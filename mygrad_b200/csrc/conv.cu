@@ -9,6 +9,7 @@
 #include "conv_gemm.cuh"
 #include "conv_tc.cuh"
 #include "conv_tma.cuh"
+#include "conv_halo.cuh"
 
 namespace mgb {
 namespace conv {
@@ -488,7 +489,159 @@ struct TmaJob {                   // one fwd-like GEMM on channels-last planes
   int P[3], pmul[3], base[3], X[3];
   long long nbatch;
   int cpad, ntaps, nout, bn, ny, rows;
+  const TapBuild* tb = nullptr;   // per-axis tap lists (host copy) — the halo kernel addresses taps by axis
 };
+
+// ---- halo-reuse variant (conv_halo.cuh): returns 0 ok, 1 error, 2 not applicable -----------
+// MGB_CONV_HALO: unset = by cost model, "0" = never, "1" = whenever the geometry allows it
+int halo_launch(const TmaJob& j, cudaStream_t st) {
+  static_assert(halo::kMaxTap >= kMaxW, "tap table too small");
+  EncodeTiledFn enc = tma_encoder();
+  const char* eh = getenv("MGB_CONV_HALO");
+  if (!enc || !tma_enabled() || !j.tb || (eh && eh[0] == '0')) return 2;
+  const bool force = eh && eh[0] == '1';
+  const TapBuild& tb = *j.tb;
+  for (int i = 0; i < 3; ++i) if (j.pmul[i] != 1 || j.X[i] < 1 || j.P[i] < 1 || tb.cnt[i] < 1) return 2;
+  if (tb.cnt[0] * tb.cnt[2] > halo::kMaxInner || tb.cnt[1] * tb.cnt[2] > halo::kMaxInner) return 2;
+  if (j.nbatch < 1) return 2;
+  const bool ncat = j.bn % 8 == 0 && 2 * j.bn <= 256;
+  const int b_stage = 2 * j.bn * 128;
+  const long long smem_cap = 227 * 1024;
+  int mind[3], maxd[3];
+  for (int i = 0; i < 3; ++i) {
+    mind[i] = maxd[i] = tb.delta[i][0];
+    for (int k = 1; k < tb.cnt[i]; ++k) { mind[i] = std::min(mind[i], (int)tb.delta[i][k]); maxd[i] = std::max(maxd[i], (int)tb.delta[i][k]); }
+  }
+  const int hc = 8 + maxd[2] - mind[2];
+  if (hc > 256) return 2;
+  // pick the row axis and the (rows, samples) split of the 16 groups with the fewest tiles
+  long long best = -1;
+  int b_ra = 1, b_bh = 16, b_bn = 1, b_plane = 0, b_bst = 0;
+  const int tiles_c = (j.P[2] + 7) / 8;
+  for (int ra = 1; ra >= 0; --ra) {
+    const int oa = 1 - ra;
+    if (ra == 0 && j.P[0] == 1) continue;                     // <= 2 spatial dims: rows are axis 1
+    for (int bh = 16; bh >= 1; bh >>= 1) {
+      const int bnb = 16 / bh;
+      if (bh > next_pow2(j.P[ra]) || bnb > next_pow2(j.nbatch)) continue;
+      const int hr = bh + maxd[ra] - mind[ra];
+      if (hr > 256) continue;
+      const long long tx = (long long)hr * bnb * hc * 128;
+      const long long plane = (tx + 1023) / 1024 * 1024;
+      const long long left = smem_cap - (1024 + 256) - halo::AST * 2 * plane;
+      const int bst = (int)std::min<long long>(6, left / b_stage);
+      if (bst < 2) continue;
+      const long long tiles = (long long)((j.P[ra] + bh - 1) / bh) * ((j.nbatch + bnb - 1) / bnb) * j.P[oa] * tiles_c;
+      // shared-memory bytes moved per tile: operand reads + filter writes per tap, halo writes per outer tap
+      const long long ntap = (long long)tb.cnt[0] * tb.cnt[1] * tb.cnt[2];
+      const long long reads = ncat ? 32768 + 384LL * j.bn : 3 * (16384 + 128LL * j.bn);
+      const long long cost = tiles * (ntap * (reads + b_stage) + (long long)tb.cnt[oa] * 2 * tx);
+      if (best < 0 || cost < best) { best = cost; b_ra = ra; b_bh = bh; b_bn = bnb; b_plane = (int)plane; b_bst = bst; }
+    }
+  }
+  if (best < 0) return 2;
+  if (!force) {
+    // the plain TMA kernel re-loads a 2 x 16 KB A tile per tap but tiles with 128-pixel boxes of any shape
+    int box[3], boxn;
+    if (choose_box(j.P, j.pmul, j.nbatch, box, &boxn)) {
+      long long tiles = (j.nbatch + boxn - 1) / boxn;
+      for (int i = 0; i < 3; ++i) tiles *= (j.P[i] + box[i] - 1) / box[i];
+      const long long ntap = (long long)tb.cnt[0] * tb.cnt[1] * tb.cnt[2];
+      const long long reads = ncat ? 32768 + 384LL * j.bn : 3 * (16384 + 128LL * j.bn);
+      const long long plain = tiles * ntap * (reads + b_stage + 32768);
+      if (best * 100 > plain * 95) return 2;
+    }
+  }
+  halo::HaloParams hp;
+  const int ra = b_ra, oa = 1 - b_ra;
+  hp.out = j.out; hp.om = j.om;
+  for (int i = 0; i < 3; ++i) {
+    hp.P[i] = j.P[i]; hp.base[i] = j.base[i]; hp.cnt[i] = tb.cnt[i];
+    for (int k = 0; k < tb.cnt[i]; ++k) hp.delta[i][k] = tb.delta[i][k];
+  }
+  hp.ra = ra; hp.oa = oa; hp.bh = b_bh; hp.bnb = b_bn;
+  hp.tiles_r = (j.P[ra] + b_bh - 1) / b_bh; hp.tiles_c = tiles_c;
+  hp.tiles_n = (int)((j.nbatch + b_bn - 1) / b_bn);
+  hp.Nbatch = (int)j.nbatch; hp.Nout = j.nout; hp.nchunk = j.cpad / 32;
+  hp.minr = mind[ra]; hp.minc = mind[2];
+  hp.hr = b_bh + maxd[ra] - mind[ra]; hp.hc = hc;
+  hp.a_plane = b_plane; hp.a_tx = hp.hr * b_bn * hc * 128;
+  {
+    const int row_pitch = b_bn * hc * 128;      // bytes between halo rows
+    for (int jr = 0; jr < tb.cnt[ra]; ++jr)
+      for (int jc = 0; jc < tb.cnt[2]; ++jc)
+        hp.tapoff[jr * tb.cnt[2] + jc] =
+            (uint32_t)((tb.delta[ra][jr] - mind[ra]) * row_pitch + (tb.delta[2][jc] - mind[2]) * 128) >> 4;
+  }
+  hp.bn = j.bn; hp.ny = j.ny; hp.bst = b_bst;
+  hp.ncat = ncat ? 1 : 0; hp.acc_cols = ncat ? 2 * j.bn : j.bn; hp.tmem_cols = pow2_cols(2 * hp.acc_cols);
+  const long long total = (long long)hp.tiles_r * hp.tiles_c * hp.tiles_n * j.P[oa] * j.ny;
+  if (total > INT32_MAX) return 2;
+  hp.total_tiles = (int)total;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  {
+    // (Cpad, X_col, N, X_row, X_outer): the halo lands as [row][sample][column][128 B]
+    const cuuint64_t sx[3] = {(cuuint64_t)j.X[1] * j.X[2] * j.cpad * 4, (cuuint64_t)j.X[2] * j.cpad * 4,
+                              (cuuint64_t)j.cpad * 4};
+    cuuint64_t dims[5] = {(cuuint64_t)j.cpad, (cuuint64_t)j.X[2], (cuuint64_t)j.nbatch, (cuuint64_t)j.X[ra],
+                          (cuuint64_t)j.X[oa]};
+    cuuint64_t strides[4] = {sx[2], sx[0] * j.X[0], sx[ra], sx[oa]};
+    cuuint32_t box[5] = {32u, (cuuint32_t)hc, (cuuint32_t)b_bn, (cuuint32_t)hp.hr, 1u};
+    cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    CUresult r1 = enc(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)j.a_hi, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)j.a_lo, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return 2;
+  }
+  {
+    long long K = (long long)j.ntaps * j.cpad;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)j.rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {32u, (cuuint32_t)j.bn};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r1 = enc(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)j.b_hi, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&mb_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)j.b_lo, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return 2;
+  }
+  size_t smem = halo::smem_bytes(hp.a_plane, j.bn, hp.bst);
+  int grid = (int)std::min<long long>(total, sm_count());
+  hp.prof = nullptr;
+  if (getenv("MGB_HALO_PROF")) {
+    // diagnostic build of the same kernel: where does the MMA thread spend its cycles?  (synchronous)
+    static unsigned long long* prof_buf = nullptr;
+    if (!prof_buf) MGB_CUDA(cudaMalloc(&prof_buf, 10 * 1024 * sizeof(unsigned long long)));
+    hp.prof = prof_buf;
+    MGB_CUDA(cudaFuncSetAttribute(halo::conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    halo::conv_halo_kernel<true><<<grid, halo::THREADS, smem, st>>>(hp, ma_hi, ma_lo, mb_hi, mb_lo);
+    MGB_LAUNCH_CHECK();
+    const double stages = (double)total / grid * hp.nchunk * tb.cnt[0] * tb.cnt[1] * tb.cnt[2];
+    const double stages_dummy = stages;
+    std::vector<unsigned long long> h(10 * 1024);
+    MGB_CUDA(cudaStreamSynchronize(st));
+    MGB_CUDA(cudaMemcpy(h.data(), prof_buf, h.size() * 8, cudaMemcpyDeviceToHost));
+    double ls = 0, ln = 0;
+    for (int i = 0; i < grid; ++i) { ls += (double)h[8 * 1024 + 2 * i]; ln += (double)h[8 * 1024 + 2 * i + 1]; }
+    fprintf(stderr, "[halo prof] B stages the MMA thread had to wait for: %.0f of %.0f per CTA, issue->ready %.0f clk\n", ln / grid, stages_dummy, ln > 0 ? ls / ln : 0.0);
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < grid; ++i) for (int k = 0; k < 8; ++k) s[k] += (double)h[8 * i + k] / grid;
+    fprintf(stderr, "[halo prof] bn=%d tiles=%d bst=%d, per tap-stage: wait A %.0f, wait B %.0f, wait tmem %.0f, "
+            "umma issue %.0f, commit %.0f, total %.0f clk; B producer: wait empty %.0f of %.0f\n", j.bn, hp.total_tiles,
+            hp.bst, s[0] / stages, s[1] / stages, s[2] / stages, s[4] / stages, s[5] / stages, s[3] / stages,
+            s[6] / stages, s[7] / stages);
+    return 0;
+  }
+  MGB_CUDA(cudaFuncSetAttribute(halo::conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  halo::conv_halo_kernel<false><<<grid, halo::THREADS, smem, st>>>(hp, ma_hi, ma_lo, mb_hi, mb_lo);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
 
 // returns 0 ok, 1 error, 2 "not applicable, use the cp.async kernel"
 int tma_launch(const TmaJob& j, cudaStream_t st) {
@@ -618,8 +771,9 @@ int tc_fwd(const Plan& p, const float* x, const float* w, float* y, const void* 
     }
     j.om.os[2] = 1; j.om.os[1] = p.G[2]; j.om.os[0] = p.G[1] * p.G[2];
     j.nbatch = p.N; j.cpad = P.cpad; j.ntaps = L.ntaps; j.nout = (int)p.F; j.bn = L.bn; j.ny = L.ny;
-    j.rows = L.rows;
-    int rc = tma_launch(j, st);
+    j.rows = L.rows; j.tb = &tb;
+    int rc = halo_launch(j, st);
+    if (rc == 2) rc = tma_launch(j, st);
     if (rc != 2) return rc;
   }
   tc::TcParams tp;
@@ -686,8 +840,9 @@ int tc_dgrad(const Plan& p, const float* dy, const float* w, float* dx, const vo
       }
       j.om.os[2] = 1; j.om.os[1] = p.X[2]; j.om.os[0] = p.X[1] * p.X[2];
       j.nbatch = p.N; j.cpad = P.cpad; j.ntaps = L.ntaps; j.nout = (int)p.C; j.bn = L.bn; j.ny = L.ny;
-      j.rows = L.rows;
-      int rc = tma_launch(j, st);
+      j.rows = L.rows; j.tb = &tb;
+      int rc = halo_launch(j, st);
+      if (rc == 2) rc = tma_launch(j, st);
       if (rc == 1) return 1;
       if (rc == 0) continue;
     }

@@ -89,6 +89,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   __trap();
 }
 
+// true in exactly one lane of a converged warp (elect.sync): unlike `lane == 0`, ptxas then knows
+// that a single thread issues the tcgen05 instructions that follow and emits them straight-line
+// instead of wrapping each one in an ELECT / broadcast loop over the active lanes
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "@P mov.s32 %0, 1;\n\t}\n"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
   int sz = pred ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
@@ -301,7 +314,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         }
       }
     }
-  } else if (lane == 0) {
+  } else if (elect_one()) {
     // ===== MMA issuer: one thread =====
     const uint32_t idesc = idesc_tf32(p.bn);
     const uint32_t smem_base = smem_u32(smem);
@@ -509,7 +522,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
         }
       }
     }
-  } else if (lane == 0) {
+  } else if (elect_one()) {
     // ===== MMA issuer =====
     const uint32_t idesc = idesc_tf32(bn) | (1u << 15) | (1u << 16);   // A and B MN-major
     const uint32_t smem_base = smem_u32(smem);

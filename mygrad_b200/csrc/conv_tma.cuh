@@ -132,7 +132,7 @@ conv_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUt
   const uint32_t smem_base = tc::smem_u32(smem);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // ===== TMA producer =====
       int it = 0;   // ring position, runs across tiles
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -158,7 +158,7 @@ conv_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // ===== MMA issuer =====
       const uint32_t idesc = tc::idesc_tf32(p.bn);
       const uint32_t idesc2 = tc::idesc_tf32(2 * p.bn);   // a_hi x [b_hi | b_lo]
@@ -381,7 +381,7 @@ conv_tma2_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // ===== TMA producer (both CTAs): own A box, own half of B; completion on the LEADER's barrier =====
       int it = 0;
       for (int pair = cluster_id; pair < p.total_tiles; pair += nclusters) {
@@ -409,7 +409,7 @@ conv_tma2_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && tc::elect_one()) {
       // ===== MMA issuer: leader CTA only, M = 256 over the pair =====
       const uint32_t idesc = (tc::idesc_tf32(p.bn) & ~(0x1Fu << 24)) | ((256u >> 4) << 24);
       int it = 0, local = 0;
@@ -564,7 +564,7 @@ wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant
   const uint32_t smem_base = tc::smem_u32(smem);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // ===== TMA producer =====
       const uint32_t tx = (uint32_t)(2 * a_plane + 2 * nvalid * WG_BLK_BYTES);
       for (int s = 0; s < S; ++s) {
@@ -612,7 +612,7 @@ wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // ===== MMA issuer: A and B MN-major, N = nvalid*32 =====
       const uint32_t idesc = tc::idesc_tf32(nvalid * 32) | (1u << 15) | (1u << 16);
       for (int s = 0; s < S; ++s) {

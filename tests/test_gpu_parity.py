@@ -213,15 +213,23 @@ TC_CASES = [
     # 3-D with an unpadded outer axis: wgrad merges (batch, axis 0) into one TMA dimension
     (3, 32, 32, (7, 8, 8), (3, 3, 3), (2, 1, 1), (0, 1, 1), 1),
     (2, 32, 48, (10, 6, 6), (2, 3, 3), (2, 1, 1), (0, 1, 0), (3, 1, 1)),
+    # stride-1 gathers with wide / dilated filters and ragged extents: the halo-reuse kernel's home turf
+    (4, 32, 64, (20, 19), (5, 5), 1, 2, 1),
+    (2, 64, 64, (17, 23), (3, 3), 1, (2, 1), (2, 3)),
+    (3, 32, 32, (40,), (7,), 1, 3, 1),
+    (17, 32, 160, (4, 5), (3, 3), 1, 1, 1),
+    (2, 32, 32, (9, 20, 12), (3, 3, 3), 1, (1, 0, 1), 1),
 ]
 
 
 @pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "x".join(map(str, c[:3])) + f"_{len(c[3])}d")
-@pytest.mark.parametrize("path", ["tma", "tma2cta", "cpasync", "mma"])
+@pytest.mark.parametrize("path", ["halo", "tma", "tma2cta", "cpasync", "mma"])
 def test_conv_f32_paths_vs_oracle(case, path, monkeypatch):
-    """every fp32 kernel family (tcgen05 fed by TMA, tcgen05 fed by cp.async, mma.sync) against the oracle"""
-    monkeypatch.setenv("MGB_CONV_F32_PATH", "tma" if path == "tma2cta" else path)
+    """every fp32 kernel family (tcgen05 fed by TMA with and without halo reuse, tcgen05 fed by
+    cp.async, mma.sync) against the oracle"""
+    monkeypatch.setenv("MGB_CONV_F32_PATH", "tma" if path in ("tma2cta", "halo") else path)
     monkeypatch.setenv("MGB_CONV_2CTA", "1" if path == "tma2cta" else "0")   # cta_group::2 variant is opt-in
+    monkeypatch.setenv("MGB_CONV_HALO", "1" if path == "halo" else "0")      # "1": wherever the geometry allows
     N, C, F, X, W, s, p, d = case
     rng = np.random.default_rng(hash(case) % (2 ** 32))
     x = rng.standard_normal((N, C, *X)).astype(np.float32)
