@@ -352,6 +352,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
           tc::tmem_ld16(lane_base + (uint32_t)(p.bn + col), u);
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+
         }
         if (rowoff >= 0) {
 #pragma unroll
