@@ -159,6 +159,35 @@ int mgb_matmul_skinny(int dtype, int which, int64_t n, int64_t d, int64_t m, con
 /* dst[i] = (*scalar) * src[i], scalar on the device — `grad * self.back` (softmax_crossentropy.py:50) */
 int mgb_scale_by(int dtype, size_t n, const void* scalar, const void* src, void* dst, void* stream);
 
+/* ---- batch normalisation --------------------------------------------
+ * x is (n, c, s): s = product of the axes after the channel axis.  Replaces
+ * BatchNorm.__call__ / backward_var (src/mygrad/nnet/layers/batchnorm.py:26-111).
+ * `moments` is 3*c float64 on the device: mean[c], population variance[c], count[c];
+ * `sums` is 2*c float64: sum(grad)[c], sum(grad * x_norm)[c].  Both stay in float64 so that a
+ * data-parallel caller can merge them across ranks before applying them. */
+int mgb_batchnorm_workspace_bytes(int64_t n, int64_t c, size_t* bytes);
+/* per-channel mean / variance over the n and s axes (batchnorm.py:56-57) */
+int mgb_batchnorm_stats(int dtype, int64_t n, int64_t c, int64_t s, const void* x, void* moments,
+                        void* ws, size_t ws_bytes, void* stream);
+/* y = (x - mean) / sqrt(var + eps) [* gamma] [+ beta]; gamma / beta (c,) may be NULL (batchnorm.py:59-73) */
+int mgb_batchnorm_fwd(int dtype, int64_t n, int64_t c, int64_t s, const void* x, const void* moments,
+                      const void* gamma, const void* beta, double eps, void* y, void* stream);
+/* sum(grad) and sum(grad * x_norm) per channel: dbeta and dgamma (batchnorm.py:102-107) and the
+ * two means the dx formula needs */
+int mgb_batchnorm_bwd_reduce(int dtype, int64_t n, int64_t c, int64_t s, const void* grad, const void* x,
+                             const void* moments, double eps, void* sums, void* ws, size_t ws_bytes,
+                             void* stream);
+/* dx = (grad - mean(grad) - x_norm * sum(grad * x_norm)/count) / std [* gamma] (batchnorm.py:76-99) */
+int mgb_batchnorm_bwd_dx(int dtype, int64_t n, int64_t c, int64_t s, const void* grad, const void* x,
+                         const void* moments, const void* sums, const void* gamma, double eps, void* dx,
+                         void* stream);
+
+/* data-parallel batch norm: merges the per-rank `moments` into the full-batch ones.  The caller
+ * runs phase 0, sum-all-reduces buf[0, 2c), runs phase 1, sum-all-reduces buf[2c, 3c), runs
+ * phase 2 (buf: 3*c float64 on the device).  The reference has no ranks; the result to match is the
+ * single-process reference on the concatenated batch. */
+int mgb_batchnorm_merge(int phase, int64_t c, void* moments, void* buf, void* stream);
+
 /* ---- runtime plumbing -------------------------------------------------- */
 
 int mgb_device_count(int* count);

@@ -73,6 +73,14 @@ __global__ void __launch_bounds__(kThreads) scale_kernel(T* __restrict__ dst, si
   for (size_t i = nv * V + tid; i < n; i += stride) dst[i] *= alpha;
 }
 
+// element-wise fallback for buffers that are not 16-byte aligned (views into a larger allocation)
+template <typename S, typename D>
+__global__ void __launch_bounds__(kThreads) cast_scalar_kernel(const S* __restrict__ src, D* __restrict__ dst,
+                                                               size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = (D)src[i];
+}
+
 template <typename S, typename D>
 __global__ void __launch_bounds__(kThreads) cast_kernel(const S* __restrict__ src,
                                                         D* __restrict__ dst, size_t n) {
@@ -324,7 +332,12 @@ extern "C" int mgb_copy_cast(int src_dtype, int dst_dtype, size_t n, const void*
     MGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
     return 0;
   }
-  if (src_dtype == MGB_F32 && dst_dtype == MGB_F64)
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  if (!aligned && src_dtype == MGB_F32 && dst_dtype == MGB_F64)
+    cast_scalar_kernel<float, double><<<grid_for(n), kThreads, 0, st>>>((const float*)src, (double*)dst, n);
+  else if (!aligned && src_dtype == MGB_F64 && dst_dtype == MGB_F32)
+    cast_scalar_kernel<double, float><<<grid_for(n), kThreads, 0, st>>>((const double*)src, (float*)dst, n);
+  else if (src_dtype == MGB_F32 && dst_dtype == MGB_F64)
     cast_kernel<float, double><<<grid_for(n / 4 + 1), kThreads, 0, st>>>((const float*)src, (double*)dst, n);
   else if (src_dtype == MGB_F64 && dst_dtype == MGB_F32)
     cast_kernel<double, float><<<grid_for(n / 4 + 1), kThreads, 0, st>>>((const double*)src, (float*)dst, n);

@@ -1,5 +1,6 @@
 """``mygrad.nnet.layers`` entry points served by the B200 path (layers/__init__.py:1-5)."""
+from .batchnorm import BatchNorm, batchnorm
 from .conv import ConvND, conv_nd
 from .pooling import MaxPoolND, MeanPoolND, max_pool, mean_pool
 
-__all__ = ["conv_nd", "max_pool", "mean_pool", "ConvND", "MaxPoolND", "MeanPoolND"]
+__all__ = ["conv_nd", "max_pool", "mean_pool", "batchnorm", "ConvND", "MaxPoolND", "MeanPoolND", "BatchNorm"]

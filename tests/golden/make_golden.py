@@ -243,8 +243,54 @@ def run_cnn_case():
 
 
 
+# ---- batchnorm (src/mygrad/nnet/layers/batchnorm.py): value, saved moments, all three grads ---------
+BN_CASES = [
+    # name, x_shape, dtype, gamma?, beta?, eps
+    ("bn_2d_affine", (6, 4), "f8", True, True, 1e-8),
+    ("bn_docstring", (3, 1), "f8", False, False, 0.0),
+    ("bn_3d_gamma_only", (4, 3, 5), "f8", True, False, 1e-5),
+    ("bn_4d_affine", (5, 6, 7, 8), "f8", True, True, 1e-5),
+    ("bn_4d_plain", (3, 4, 6, 6), "f8", False, False, 1e-3),
+    ("bn_4d_beta_only", (3, 4, 5, 6), "f8", False, True, 1e-6),
+    ("bn_4d_f32", (8, 16, 12, 12), "f4", True, True, 1e-5),
+    ("bn_5d_f32", (2, 3, 4, 5, 6), "f4", True, True, 1e-5),
+    ("bn_offset_mean", (16, 3, 9, 9), "f8", True, True, 1e-8),     # mean >> std: variance must not cancel
+    ("bn_odd_run", (3, 5, 7, 3), "f4", True, True, 1e-5),          # run length 21: scalar (unvectorised) path
+]
+
+
+def run_bn_cases():
+    from mygrad.nnet.layers import batchnorm
+
+    out, manifest = {}, {}
+    for i, (name, xs, dt, has_g, has_b, eps) in enumerate(BN_CASES):
+        x = rng_arr(700 + i, xs, dt)
+        if name == "bn_docstring":
+            x = np.array([1.0, 4.0, 1.0]).reshape(3, 1)          # batchnorm.py:152-157
+        if name == "bn_offset_mean":
+            x = x * 1e-3 + 1e3
+        c = xs[1]
+        gamma = mg.Tensor(rng_arr(800 + i, (c,), dt) + 1) if has_g else None
+        beta = mg.Tensor(rng_arr(900 + i, (c,), dt)) if has_b else None
+        xt = mg.Tensor(x)
+        y = batchnorm(xt, gamma=gamma, beta=beta, eps=eps)
+        op = y.creator
+        g = rng_arr(1000 + i, y.shape, dt)
+        y.backward(g)
+        out[f"{name}/x"], out[f"{name}/g"], out[f"{name}/y"], out[f"{name}/dx"] = x, g, y.data, xt.grad
+        out[f"{name}/mean"], out[f"{name}/var"] = op.mean, op.var
+        if has_g:
+            out[f"{name}/gamma"], out[f"{name}/dgamma"] = gamma.data, gamma.grad
+        if has_b:
+            out[f"{name}/beta"], out[f"{name}/dbeta"] = beta.data, beta.grad
+        manifest[name] = {"eps": eps}
+    np.savez_compressed(HERE / "batchnorm_cases.npz", manifest=json.dumps(manifest), **out)
+    return len(manifest)
+
+
 if __name__ == "__main__":
     print("reference:", mg.__file__)
+    print("batchnorm cases:", run_bn_cases())
     print("conv cases:", run_conv_cases())
     print("pool cases:", run_pool_cases())
     print("layer cases:", run_layer_cases())

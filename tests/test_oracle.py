@@ -6,7 +6,7 @@ import json
 import numpy as np
 import pytest
 
-from conftest import assert_close
+from conftest import GoldenFile, assert_close
 from oracle import conv_pool_oracle as oc
 
 
@@ -174,3 +174,36 @@ def test_oracle_rejects_incompatible_shapes():
     assert oc.conv_fwd(np.zeros((1, 2, 65, 65)), np.zeros((3, 2, 5, 5)), 2, 0, 2).shape == (1, 3, 29, 29)
     with pytest.raises(ValueError):
         oc.max_pool_fwd(np.zeros((1, 2, 2, 2)), (3, 3, 3), 1)
+
+
+# ---- batchnorm -------------------------------------------------------------
+
+def test_batchnorm_docstring_example():
+    # src/mygrad/nnet/layers/batchnorm.py:152-157
+    x = np.array([1.0, 4.0, 1.0]).reshape(3, 1)
+    y, mean, var = oc.batchnorm_fwd(x, None, None, 0.0)
+    np.testing.assert_allclose(y[:, 0], [-0.70710678, 1.41421356, -0.70710678], rtol=1e-8)
+    np.testing.assert_allclose(mean, [2.0])
+    np.testing.assert_allclose(var, [2.0])
+
+
+@pytest.mark.parametrize("name", GoldenFile("batchnorm_cases.npz").names())
+def test_batchnorm_oracle_vs_golden(name):
+    gf = GoldenFile("batchnorm_cases.npz")
+    c, eps = gf.case(name), gf.manifest[name]["eps"]
+    x, g = c["x"], c["g"]
+    dt = x.dtype
+    y, mean, var = oc.batchnorm_fwd(x, c.get("gamma"), c.get("beta"), eps)
+    # the offset-mean case amplifies rounding of the mean by mean/std = 1e6
+    loose = 1e6 if name == "bn_offset_mean" else 1.0
+    tol = dict(rtol=(1e-10 if dt == np.float64 else 2e-5) * loose, atol=(1e-12 if dt == np.float64 else 1e-6) * loose)
+    np.testing.assert_allclose(y, c["y"], **tol)
+    np.testing.assert_allclose(mean, c["mean"], rtol=1e-12 if dt == np.float64 else 1e-6)
+    np.testing.assert_allclose(var, c["var"], rtol=1e-9 if dt == np.float64 else 1e-5)
+    dx, dgamma, dbeta = oc.batchnorm_bwd(g, x, c.get("gamma"), eps)
+    scale = float(np.abs(c["dx"]).max()) or 1.0
+    np.testing.assert_allclose(dx, c["dx"], rtol=tol["rtol"], atol=tol["rtol"] * scale * 10)
+    if "dgamma" in c:
+        np.testing.assert_allclose(dgamma, c["dgamma"], rtol=tol["rtol"] * 10, atol=tol["atol"] * 100)
+    if "dbeta" in c:
+        np.testing.assert_allclose(dbeta, c["dbeta"], rtol=tol["rtol"] * 10, atol=tol["atol"] * 100)
