@@ -159,6 +159,12 @@ int mgb_matmul_skinny(int dtype, int which, int64_t n, int64_t d, int64_t m, con
 /* dst[i] = (*scalar) * src[i], scalar on the device — `grad * self.back` (softmax_crossentropy.py:50) */
 int mgb_scale_by(int dtype, size_t n, const void* scalar, const void* src, void* dst, void* stream);
 
+/* dst (G..., lead, W...) = windows of src (lead, X...) over its nd (1..3) trailing axes,
+ * G = (X - ((W-1)*dil + 1)) / step + 1 — sliding_window_view (src/mygrad/nnet/layers/utils.py:7-228),
+ * materialised because device arrays carry no strides.  The conv kernels never call this. */
+int mgb_window_gather(int dtype, int nd, int64_t lead, const int64_t* x, const int64_t* w,
+                      const int64_t* step, const int64_t* dil, const void* src, void* dst, void* stream);
+
 /* ---- batch normalisation --------------------------------------------
  * x is (n, c, s): s = product of the axes after the channel axis.  Replaces
  * BatchNorm.__call__ / backward_var (src/mygrad/nnet/layers/batchnorm.py:26-111).

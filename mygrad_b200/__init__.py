@@ -34,6 +34,7 @@ from . import nnet
 from .host import HostLayerPipeline
 from .nnet.layers import conv_nd, max_pool, mean_pool
 from .math_ops import add, matmul, reshape
+from ._io import load, save
 
 execute_op = Tensor._op  # same alias as mygrad.execute_op (src/mygrad/__init__.py:52)
 
@@ -44,5 +45,6 @@ __all__ = [
     "DeviceArray", "asdevice", "empty", "zeros", "full", "full_like", "pinned_empty",
     "current_stream", "set_stream", "synchronize", "device_available", "empty_cache",
     "InvalidGradient", "InvalidBackprop", "DisconnectedView", "SkipGradient",
-    "nnet", "conv_nd", "max_pool", "mean_pool", "add", "matmul", "reshape", "HostLayerPipeline", "lib", "LIB_PATH",
+    "nnet", "conv_nd", "max_pool", "mean_pool", "add", "matmul", "reshape", "save", "load", "HostLayerPipeline",
+    "lib", "LIB_PATH",
 ]

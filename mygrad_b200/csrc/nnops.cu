@@ -185,6 +185,33 @@ __global__ void __launch_bounds__(kThreads) softmax_xent_finish(const double* __
   if (threadIdx.x == 0) loss[0] = (T)(sh[0] / (double)N);
 }
 
+
+// out[g0, g1, g2, lead, w0, w1, w2] = src[lead, g*step + w*dil]  (sliding_window_view,
+// src/mygrad/nnet/layers/utils.py:198-228, materialised: device arrays have no strided views)
+struct WindowGeom {
+  long long lead, X[3], G[3], W[3], step[3], dil[3];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) window_gather_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                                 WindowGeom g, long long total) {
+  const long long wp = g.W[0] * g.W[1] * g.W[2];
+  const long long xs1 = g.X[2], xs0 = g.X[1] * g.X[2], xp = g.X[0] * xs0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const long long w = t % wp; t /= wp;
+    const long long l = t % g.lead; t /= g.lead;
+    const long long g2 = t % g.G[2]; t /= g.G[2];
+    const long long g1 = t % g.G[1];
+    const long long g0 = t / g.G[1];
+    const long long w2 = w % g.W[2], w1 = (w / g.W[2]) % g.W[1], w0 = w / (g.W[2] * g.W[1]);
+    const long long x0 = g0 * g.step[0] + w0 * g.dil[0], x1 = g1 * g.step[1] + w1 * g.dil[1],
+                    x2 = g2 * g.step[2] + w2 * g.dil[2];
+    dst[i] = src[l * xp + x0 * xs0 + x1 * xs1 + x2];
+  }
+}
+
 }  // namespace
 }  // namespace mgb
 
@@ -475,4 +502,34 @@ extern "C" int mgb_matmul_skinny(int dtype, int which, int64_t n, int64_t d, int
   if (dtype == MGB_F32)
     return skinny_t<float>(which, n, (int)d, (int)m, (const float*)a, (const float*)b, (float*)out, as_stream(stream));
   return skinny_t<double>(which, n, (int)d, (int)m, (const double*)a, (const double*)b, (double*)out, as_stream(stream));
+}
+
+extern "C" int mgb_window_gather(int dtype, int nd, int64_t lead, const int64_t* x, const int64_t* w,
+                                 const int64_t* step, const int64_t* dil, const void* src, void* dst,
+                                 void* stream) {
+  if (nd < 1 || nd > 3) return fail("mgb_window_gather: %d windowed axes (1..3 supported)", nd);
+  WindowGeom g;
+  g.lead = lead;
+  long long total = lead;
+  for (int i = 0; i < 3; ++i) {              // right-align the windowed axes in 3 slots
+    int j = i - (3 - nd);
+    g.X[i] = j >= 0 ? x[j] : 1; g.W[i] = j >= 0 ? w[j] : 1;
+    g.step[i] = j >= 0 ? step[j] : 1; g.dil[i] = j >= 0 ? dil[j] : 1;
+    if (g.W[i] < 1 || g.step[i] < 1 || g.dil[i] < 1) return fail("mgb_window_gather: bad window/step/dilation");
+    long long span = (g.W[i] - 1) * g.dil[i] + 1;
+    if (span > g.X[i]) return fail("mgb_window_gather: window does not fit axis %d", j);
+    g.G[i] = (g.X[i] - span) / g.step[i] + 1;
+    total *= g.G[i] * g.W[i];
+  }
+  if (total == 0) return 0;
+  if (!src || !dst) return fail("mgb_window_gather: null");
+  cudaStream_t st = as_stream(stream);
+  if (dtype == MGB_F32)
+    window_gather_kernel<float><<<grid_for((size_t)total), kThreads, 0, st>>>((const float*)src, (float*)dst, g, total);
+  else if (dtype == MGB_F64)
+    window_gather_kernel<double><<<grid_for((size_t)total), kThreads, 0, st>>>((const double*)src, (double*)dst, g, total);
+  else
+    return fail("mgb_window_gather: bad dtype %d", dtype);
+  MGB_LAUNCH_CHECK();
+  return 0;
 }

@@ -288,8 +288,35 @@ def run_bn_cases():
     return len(manifest)
 
 
+# ---- on-disk format and the public window view ---------------------------------
+def run_io_and_window_cases():
+    # a file written by the reference's own mg.save (src/mygrad/_io.py:54-63): data + grad keys
+    x = mg.arange(10.0)
+    (x * x).backward()
+    mg.save(HERE / "saved_by_reference.npz", x)
+    y = mg.Tensor(rng_arr(41, (3, 4), "f4"))
+    mg.save(HERE / "saved_by_reference_nograd.npz", y)
+    # sliding_window_view values (utils.py:7-228) incl. the docstring example (utils.py:60-97)
+    out, manifest = {}, {}
+    cases = [
+        ("doc_example", np.arange(36.0).reshape(6, 6), (3, 2), (2, 2), None),
+        ("w1d_step2", rng_arr(42, (3, 11), "f8"), (4,), 2, None),
+        ("w2d_dilated", rng_arr(43, (2, 3, 9, 10), "f4"), (2, 3), (2, 1), (3, 2)),
+        ("w3d", rng_arr(44, (2, 5, 6, 7), "f8"), (2, 3, 2), (1, 2, 3), None),
+        ("w3d_dil_int", rng_arr(45, (7, 8, 9), "f4"), (2, 2, 2), 2, 2),
+        ("no_lead", rng_arr(46, (8, 9), "f8"), (3, 3), 3, None),
+    ]
+    for name, arr, win, step, dil in cases:
+        out[f"{name}/x"] = arr
+        out[f"{name}/view"] = np.ascontiguousarray(sliding_window_view(arr, win, step, dil))
+        manifest[name] = {"window_shape": win, "step": step, "dilation": dil}
+    np.savez_compressed(HERE / "window_cases.npz", manifest=json.dumps(manifest), **out)
+    return len(manifest)
+
+
 if __name__ == "__main__":
     print("reference:", mg.__file__)
+    print("io / window cases:", run_io_and_window_cases())
     print("batchnorm cases:", run_bn_cases())
     print("conv cases:", run_conv_cases())
     print("pool cases:", run_pool_cases())
