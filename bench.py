@@ -372,8 +372,28 @@ def run_ours(args, cfg, name):
             check(lib.mgb_event_record(b, stream))
             return elapsed(a, b) / reps
 
-        phases["conv_fwd"] = {"ms": timed(lambda: check(lib.mgb_conv_fwd(
-            C.byref(cd), P(x_dev), P(w_dev), P(y), P(wss[0][0]), wss[0][1], stream))), "flops": geo["flops"]}
+        # the step builds the channels-last operand planes of the tensor-core path ONCE per tensor
+        # (x planes: fwd + dW, dy planes: dX + dW; ConvND keeps them between forward and backward), so
+        # the phases time the same entry points the step calls: plane prep on its own (HBM-bound), then
+        # the *_p kernels on prebuilt planes.  float64 has no planes (bytes = 0, NULL).
+        def planes_for(tensor, src):
+            n = C.c_size_t(0)
+            check(lib.mgb_conv_planes_bytes(C.byref(cd), tensor, C.byref(n)))
+            if n.value == 0:
+                return None, None
+            buf = mg.empty(((n.value + 7) // 8,), np.float64)
+            ms = timed(lambda: check(lib.mgb_conv_make_planes(C.byref(cd), tensor, P(src), P(buf), stream)))
+            return buf, ms
+
+        PN = lambda a: C.c_void_p(a.ptr if a is not None else 0)
+        x_planes, ms_px = planes_for(0, x_dev)
+        dy_planes, ms_pdy = planes_for(1, gy)
+        if ms_px is not None:
+            phases["plane_prep_x"] = {"ms": ms_px, "bytes": 3 * geo["x_bytes"]}        # read x, write hi + lo
+            phases["plane_prep_dy"] = {"ms": ms_pdy, "bytes": 3 * geo["y_bytes"]}
+        phases["conv_fwd"] = {"ms": timed(lambda: check(lib.mgb_conv_fwd_p(
+            C.byref(cd), P(x_dev), P(w_dev), P(y), PN(x_planes), P(wss[0][0]), wss[0][1], stream))),
+            "flops": geo["flops"]}
         if cfg["pool"]:
             npool = len(cfg["pool"])
             pd = PoolDesc()
@@ -388,10 +408,12 @@ def run_ours(args, cfg, name):
                                   "bytes": geo["y_bytes"] + geo["p_bytes"]}
             phases["pool_bwd"] = {"ms": timed(lambda: check(lib.mgb_pool_bwd(C.byref(pd), P(gp), P(y), P(gy), stream))),
                                   "bytes": 2 * geo["y_bytes"] + geo["p_bytes"]}
-        phases["conv_dgrad"] = {"ms": timed(lambda: check(lib.mgb_conv_dgrad(
-            C.byref(cd), P(gy), P(w_dev), P(dx), P(wss[1][0]), wss[1][1], stream))), "flops": geo["flops"]}
-        phases["conv_wgrad"] = {"ms": timed(lambda: check(lib.mgb_conv_wgrad(
-            C.byref(cd), P(gy), P(x_dev), P(dw), P(wss[2][0]), wss[2][1], stream))), "flops": geo["flops"]}
+        phases["conv_dgrad"] = {"ms": timed(lambda: check(lib.mgb_conv_dgrad_p(
+            C.byref(cd), P(gy), P(w_dev), P(dx), PN(dy_planes), P(wss[1][0]), wss[1][1], stream))),
+            "flops": geo["flops"]}
+        phases["conv_wgrad"] = {"ms": timed(lambda: check(lib.mgb_conv_wgrad_p(
+            C.byref(cd), P(gy), P(x_dev), P(dw), PN(dy_planes), PN(x_planes), P(wss[2][0]), wss[2][1], stream))),
+            "flops": geo["flops"]}
 
     # ---- measured ceilings -----------------------------------------------------------------------
     peaks = {}
