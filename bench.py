@@ -257,9 +257,10 @@ def run_ours(args, cfg, name):
         xt, wt = Tensor(xd, copy=False), Tensor(wd, copy=False)
         y = conv_nd(xt, wt, **conv_kw)
         o = max_pool(y, cfg["pool"], 2) if cfg["pool"] else y
-        o.backward()
+        with dp.fused_wgrad() as fused:     # dW: split-K reduction + cross-rank sum in one kernel
+            o.backward()
         if world > 1:
-            dp.allreduce([wt.grad])
+            dp.allreduce([wt.grad], summed=[wt.grad] if fused.peer_slot_bytes else [])
         return o, xt, wt
 
     def events():
@@ -338,6 +339,34 @@ def run_ours(args, cfg, name):
                "d2h_bytes_per_step": int(sum(r.nbytes for r in res)),
                "api": f"HostLayerPipeline.step (chunks={args.e2e_chunks}; H2D/compute/D2H overlapped)"}
         pipe.close()
+        # what bounds this number: the pinned-memory PCIe rate of the box, measured here (one direction
+        # alone and both at once); the step moves d2h_bytes out while h2d_bytes come in
+        nb = 256 << 20
+        hb_in, hb_out = mg.pinned_empty((nb // 4,), np.float32), mg.pinned_empty((nb // 4,), np.float32)
+        db_in, db_out = mg.empty((nb // 4,), np.float32), mg.empty((nb // 4,), np.float32)
+        s1, s2 = C.c_void_p(), C.c_void_p()
+        check(lib.mgb_stream_create(C.byref(s1))); check(lib.mgb_stream_create(C.byref(s2)))
+
+        def copies(h2d: bool, d2h: bool, reps: int = 4) -> float:
+            def go():
+                if h2d:
+                    check(lib.mgb_memcpy_h2d(C.c_void_p(db_in.ptr), C.c_void_p(hb_in.ctypes.data), C.c_size_t(nb), s1))
+                if d2h:
+                    check(lib.mgb_memcpy_d2h(C.c_void_p(hb_out.ctypes.data), C.c_void_p(db_out.ptr), C.c_size_t(nb), s2))
+            go()
+            check(lib.mgb_stream_synchronize(s1)); check(lib.mgb_stream_synchronize(s2))
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                go()
+            check(lib.mgb_stream_synchronize(s1)); check(lib.mgb_stream_synchronize(s2))
+            return nb * reps / (time.perf_counter() - t0) / 1e9
+
+        pcie = {"h2d_gbs": copies(True, False), "d2h_gbs": copies(False, True), "both_each_gbs": copies(True, True)}
+        lib.mgb_stream_destroy(s1); lib.mgb_stream_destroy(s2)
+        e2e["pcie"] = pcie
+        e2e["d2h_gbs_achieved"] = e2e["d2h_bytes_per_step"] / (e2e_ms * 1e-3) / 1e9
+        e2e["bound"] = "PCIe: frac = achieved D2H rate / measured D2H rate with both directions busy"
+        e2e["frac_of_pcie"] = e2e["d2h_gbs_achieved"] / pcie["both_each_gbs"]
 
     # ---- per-phase timing: which kernel dominates, and its roofline -------------------------
     # (straight through the C ABI with preallocated outputs, so that only kernels are timed)
@@ -520,9 +549,11 @@ def run_c5(args):
         h = max_pool(relu(conv_nd(x, p["w1"], stride=1, padding=1) + p["b1"]), (2, 2), 2)
         h = max_pool(relu(conv_nd(h, p["w2"], stride=1, padding=1) + p["b2"]), (2, 2), 2)
         loss = softmax_crossentropy(h.reshape(B, -1) @ p["wd"] + p["bd"], labels)
-        loss.backward()
+        with dp.fused_wgrad() as fused:
+            loss.backward()
         if world > 1:   # the loss averages over the local batch: rescale so the sum is the global mean
-            dp.allreduce([t.grad for t in p.values()], scale=scale_for_mean_loss(B, B * world))
+            dp.allreduce([t.grad for t in p.values()], scale=scale_for_mean_loss(B, B * world),
+                         summed=[p["w1"].grad, p["w2"].grad] if fused.peer_slot_bytes else [])
         return loss, p
 
     def barrier():

@@ -234,6 +234,26 @@ int mgb_comm_destroy(void);
 /* in-place sum all-reduce of a gradient buffer (dW, bias grads) */
 int mgb_allreduce_sum(void* buf, size_t n, int dtype, void* stream);
 
+/* Peer-memory collective (our own, over NVLink / NVSwitch): every rank allocates one region
+ * (flags + two data slots of slot_bytes) and maps every other rank's region with CUDA IPC.
+ *   mgb_peer_create  -> 64-byte IPC handle of this rank's region (ship it to all ranks);
+ *   mgb_peer_connect <- the world_size handles in rank order (world_size * 64 bytes);
+ *   mgb_peer_allreduce_sum: in-place sum over ranks of n elements (n * itemsize <= slot_bytes), one
+ *     kernel: publish -> flag exchange -> peer loads, summed in rank order in float64, so every rank
+ *     holds bit-identical results.  Calls are collective and must be issued in the same order on
+ *     every rank.
+ *   mgb_conv_wgrad_dp: mgb_conv_wgrad_p whose final split-K reduction ALSO sums over the ranks in
+ *     the same kernel (the fused form of "dW = ConvND.backward_var(grad, 1)" + all-reduce; the
+ *     reference has no ranks).  Without a connected peer group it is mgb_conv_wgrad_p. */
+int mgb_peer_create(int rank, int world_size, size_t slot_bytes, void* ipc_handle64);
+int mgb_peer_connect(const void* handles);
+int mgb_peer_destroy(void);
+int mgb_peer_slot_bytes(size_t* bytes);
+int mgb_peer_allreduce_sum(void* buf, size_t n, int dtype, void* stream);
+int mgb_conv_wgrad_dp(const mgb_conv_desc* d, const void* dy, const void* x, void* dw,
+                      const void* dy_planes, const void* x_planes, void* ws, size_t ws_bytes,
+                      void* stream);
+
 /* ---- measurement helpers (bench.py only) ---------------------------------- */
 
 /* Register-resident MMA loops that measure the tensor-pipe ceilings the

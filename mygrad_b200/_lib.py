@@ -117,6 +117,12 @@ EXPORTS = {
     "mgb_comm_init_rank": (_i, [_vp, _i, _i]),
     "mgb_comm_destroy": (_i, []),
     "mgb_allreduce_sum": (_i, [_vp, _sz, _i, _vp]),
+    "mgb_peer_create": (_i, [_i, _i, _sz, _vp]),
+    "mgb_peer_connect": (_i, [_vp]),
+    "mgb_peer_destroy": (_i, []),
+    "mgb_peer_slot_bytes": (_i, [C.POINTER(_sz)]),
+    "mgb_peer_allreduce_sum": (_i, [_vp, _sz, _i, _vp]),
+    "mgb_conv_wgrad_dp": (_i, [_cdp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mgb_probe_mma_peak": (_i, [_i, _i, C.POINTER(C.c_double), _vp]),
 }
 

@@ -60,10 +60,181 @@ int load_nccl() {
     if (r__ != 0) return fail("%s -> NCCL error %d: %s", #call, r__, g_nccl.GetErrorString(r__)); \
   } while (0)
 
+// ---- peer-memory all-reduce: OUR collective over NVLink / NVSwitch -----------------------------
+//
+// dW (and every broadcast-parameter grad) is a few hundred KB: an all-reduce of that size is pure
+// latency, and it always follows a small reduction of our own (the split-K partials of the wgrad
+// GEMM).  peer_reduce_allreduce does both in ONE kernel: every rank owns a cudaMalloc'ed region
+// (flags + two data slots) that all other ranks map with CUDA IPC; CTA c of rank r
+//   A. sums its chunk of the local split-K partials (float64, fixed order) into rank r's slot,
+//   B. publishes "chunk c of rank r, epoch e" into every peer's flag array (release, system scope)
+//      and waits until its own flag array shows epoch e for chunk c from every rank,
+//   C. reads chunk c of every rank's slot over NVLink (peer loads) and adds them in RANK ORDER in
+//      float64 — every rank computes bit-identical sums — and writes the result.
+// Chunks only depend on the same chunk index on the other GPUs, so there is no grid-wide barrier;
+// slots alternate with the epoch parity: a rank can only start epoch e+2 after every peer has
+// published e+1, i.e. finished reading epoch e (kernels of one rank run in stream order).
+
+constexpr int kPeerMaxWorld = 16;
+constexpr int kPeerChunks = 128;            // CTAs per call == flag slots per source rank
+constexpr size_t kPeerFlagBytes = (size_t)kPeerMaxWorld * kPeerChunks * sizeof(uint32_t);
+
+struct PeerTable {
+  char* base[kPeerMaxWorld];                // region of each rank as mapped into THIS process
+};
+
+struct PeerState {
+  bool ready = false;
+  int rank = 0, world = 1;
+  size_t slot_bytes = 0;
+  char* local = nullptr;
+  PeerTable table{};
+  uint32_t epoch = 0;
+};
+PeerState g_peer;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T ld_peer(const T* p) {      // peer memory: never through a stale L1 line
+  return *reinterpret_cast<const volatile T*>(p);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) peer_reduce_allreduce_kernel(const T* partial, int splits,
+                                                                    long long n, T* out,
+                                                                    PeerTable tab, int rank, int world,
+                                                                    size_t slot_off, uint32_t epoch) {
+  const int c = blockIdx.x;
+  const long long per = (n + kPeerChunks - 1) / kPeerChunks;
+  const long long lo = (long long)c * per, hi = min(n, lo + per);
+  T* mine = reinterpret_cast<T*>(tab.base[rank] + kPeerFlagBytes + slot_off);
+  // A: local split-K reduction into this rank's slot
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    double acc = 0.0;
+    for (int s = 0; s < splits; ++s) acc += (double)partial[(long long)s * n + i];
+    mine[i] = (T)acc;
+  }
+  __threadfence_system();
+  __syncthreads();
+  // B: publish chunk c to every rank (own flag array included), then wait for every rank's chunk c
+  if (threadIdx.x < world) {
+    uint32_t* flag = reinterpret_cast<uint32_t*>(tab.base[threadIdx.x]) + rank * kPeerChunks + c;
+    st_release_sys(flag, epoch);
+  }
+  if (threadIdx.x < world) {
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(tab.base[rank]) + threadIdx.x * kPeerChunks + c;
+    unsigned long long spin = 0;
+    while (ld_acquire_sys(flag) != epoch) {
+      if (++spin > (1ull << 31)) __trap();          // a peer that never arrives must not hang the GPU
+    }
+  }
+  __syncthreads();
+  // C: sum the chunk over ranks in rank order
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    double acc = 0.0;
+    for (int r = 0; r < world; ++r)
+      acc += (double)ld_peer(reinterpret_cast<const T*>(tab.base[r] + kPeerFlagBytes + slot_off) + i);
+    out[i] = (T)acc;
+  }
+}
+
 }  // namespace
+
+// used by the wgrad epilogue (conv.cu) and by mgb_peer_allreduce_sum
+bool peer_ready() { return g_peer.ready && g_peer.world > 1; }
+
+int peer_reduce_allreduce(int dtype, const void* partial, int splits, long long n, void* out, cudaStream_t st) {
+  if (!peer_ready()) return fail("peer all-reduce: mgb_peer_connect has not been called");
+  const size_t esz = dtype == MGB_F32 ? 4 : 8;
+  if ((size_t)n * esz > g_peer.slot_bytes)
+    return fail("peer all-reduce: %lld elements exceed the %zu-byte slot", n, g_peer.slot_bytes);
+  if (n == 0) return 0;
+  const uint32_t epoch = ++g_peer.epoch;
+  const size_t slot_off = (epoch & 1u) ? g_peer.slot_bytes : 0;
+  if (dtype == MGB_F32)
+    peer_reduce_allreduce_kernel<float><<<kPeerChunks, 256, 0, st>>>((const float*)partial, splits, n, (float*)out,
+                                                                    g_peer.table, g_peer.rank, g_peer.world,
+                                                                    slot_off, epoch);
+  else if (dtype == MGB_F64)
+    peer_reduce_allreduce_kernel<double><<<kPeerChunks, 256, 0, st>>>((const double*)partial, splits, n,
+                                                                     (double*)out, g_peer.table, g_peer.rank,
+                                                                     g_peer.world, slot_off, epoch);
+  else
+    return fail("peer all-reduce: bad dtype %d", dtype);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace mgb
 
 using namespace mgb;
+
+extern "C" int mgb_peer_create(int rank, int world_size, size_t slot_bytes, void* ipc_handle64) {
+  if (world_size < 1 || world_size > kPeerMaxWorld || rank < 0 || rank >= world_size || !ipc_handle64)
+    return fail("mgb_peer_create: bad arguments (world=%d rank=%d, at most %d ranks)", world_size, rank,
+                kPeerMaxWorld);
+  if (g_peer.local) return fail("mgb_peer_create: already created");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  slot_bytes = align_up(slot_bytes, 256);
+  const size_t total = kPeerFlagBytes + 2 * slot_bytes;
+  void* ptr = nullptr;
+  MGB_CUDA(cudaMalloc(&ptr, total));
+  MGB_CUDA(cudaMemset(ptr, 0, total));
+  MGB_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) {
+    cudaFree(ptr);
+    return fail("cudaIpcGetMemHandle -> %s", cudaGetErrorString(e));
+  }
+  memcpy(ipc_handle64, &h, sizeof(h));
+  g_peer.local = (char*)ptr;
+  g_peer.rank = rank; g_peer.world = world_size; g_peer.slot_bytes = slot_bytes; g_peer.epoch = 0;
+  return 0;
+}
+
+extern "C" int mgb_peer_connect(const void* handles) {
+  if (!g_peer.local || !handles) return fail("mgb_peer_connect: mgb_peer_create first");
+  for (int r = 0; r < g_peer.world; ++r) {
+    if (r == g_peer.rank) { g_peer.table.base[r] = g_peer.local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail("cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
+    g_peer.table.base[r] = (char*)p;
+  }
+  g_peer.ready = true;
+  return 0;
+}
+
+extern "C" int mgb_peer_destroy(void) {
+  if (!g_peer.local) return 0;
+  cudaDeviceSynchronize();
+  if (g_peer.ready)
+    for (int r = 0; r < g_peer.world; ++r)
+      if (r != g_peer.rank && g_peer.table.base[r]) cudaIpcCloseMemHandle(g_peer.table.base[r]);
+  cudaFree(g_peer.local);
+  g_peer = PeerState{};
+  return 0;
+}
+
+extern "C" int mgb_peer_slot_bytes(size_t* bytes) {
+  if (!bytes) return fail("mgb_peer_slot_bytes: null");
+  *bytes = peer_ready() ? g_peer.slot_bytes : 0;
+  return 0;
+}
+
+extern "C" int mgb_peer_allreduce_sum(void* buf, size_t n, int dtype, void* stream) {
+  return peer_reduce_allreduce(dtype, buf, 1, (long long)n, buf, as_stream(stream));
+}
 
 extern "C" int mgb_comm_unique_id(void* id128) {
   if (!id128) return fail("mgb_comm_unique_id: null");

@@ -40,4 +40,8 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int sm_count();  // cached multiprocessor count of the current device
 
+// comm.cu: fused "sum `splits` partials of n elements, then sum over ranks through peer memory"
+bool peer_ready();
+int peer_reduce_allreduce(int dtype, const void* partial, int splits, long long n, void* out, cudaStream_t st);
+
 }  // namespace mgb

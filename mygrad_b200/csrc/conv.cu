@@ -138,6 +138,21 @@ __global__ void splitk_reduce(const T* __restrict__ partial, T* __restrict__ out
   }
 }
 
+// set by mgb_conv_wgrad_dp for the duration of the call: the split-K reduction then also sums over
+// the data-parallel ranks (comm.cu: one kernel over NVLink peer memory instead of reduce + ncclAllReduce)
+thread_local bool g_wgrad_dp = false;
+
+inline int small_grid(long long n);
+
+template <typename T>
+int finish_dw(const T* partial, T* dw, long long n, int splits, cudaStream_t st) {
+  if (g_wgrad_dp && peer_ready())
+    return peer_reduce_allreduce(sizeof(T) == 4 ? MGB_F32 : MGB_F64, partial, splits, n, dw, st);
+  splitk_reduce<T><<<small_grid(n), 256, 0, st>>>(partial, dw, n, splits);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
 inline int small_grid(long long n) {
   long long b = (n + 255) / 256;
   long long cap = (long long)sm_count() * 8;
@@ -981,7 +996,10 @@ int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, const vo
              const void* x_planes, void* ws, size_t ws_bytes, cudaStream_t st) {
   long long n_dw = p.F * p.C * p.Wp;
   if (n_dw == 0) return 0;
-  if (p.N * p.Gp == 0) { MGB_CUDA(cudaMemsetAsync(dw, 0, (size_t)n_dw * sizeof(float), st)); return 0; }
+  if (p.N * p.Gp == 0) {   // an empty shard still takes part in the cross-rank sum
+    MGB_CUDA(cudaMemsetAsync(dw, 0, (size_t)n_dw * sizeof(float), st));
+    return (g_wgrad_dp && peer_ready()) ? finish_dw<float>(dw, dw, n_dw, 1, st) : 0;
+  }
   TcWgradLayout L = tc_wgrad_layout(p);
   if (ws_bytes < L.end || !ws) return fail("conv wgrad: workspace %zu < %zu bytes", ws_bytes, L.end);
   char* base = (char*)ws;
@@ -1016,9 +1034,7 @@ int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, const vo
     int rc = wgrad_tma_launch(p, L, xhi, xlo, yhi, ylo, taps, partial, st);
     if (rc == 1) return 1;
     if (rc == 0) {
-      splitk_reduce<float><<<small_grid(n_dw), 256, 0, st>>>(partial, dw, n_dw, L.tma_splits);
-      MGB_LAUNCH_CHECK();
-      return 0;
+      return finish_dw<float>(partial, dw, n_dw, L.tma_splits, st);
     }
   }
   constexpr int STAGES = 4;
@@ -1028,9 +1044,7 @@ int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, const vo
   dim3 grid(L.mt, L.nt, L.splits);
   tc::wgrad_tc_kernel<STAGES><<<grid, tc::THREADS, smem, st>>>(wp);
   MGB_LAUNCH_CHECK();
-  splitk_reduce<float><<<small_grid(n_dw), 256, 0, st>>>(partial, dw, n_dw, L.splits);
-  MGB_LAUNCH_CHECK();
-  return 0;
+  return finish_dw<float>(partial, dw, n_dw, L.splits, st);
 }
 
 // ---- the three convolutions ------------------------------------------------------------
@@ -1104,7 +1118,10 @@ int wgrad_t(const Plan& p, const T* dy, const T* x, T* dw, void* ws, size_t ws_b
             cudaStream_t st) {
   int M = (int)p.F, N = (int)(p.C * p.Wp), K = (int)(p.N * p.Gp);
   if ((long long)M * N == 0) return 0;
-  if (K == 0) { MGB_CUDA(cudaMemsetAsync(dw, 0, (size_t)M * N * sizeof(T), st)); return 0; }
+  if (K == 0) {   // an empty shard still takes part in the cross-rank sum
+    MGB_CUDA(cudaMemsetAsync(dw, 0, (size_t)M * N * sizeof(T), st));
+    return (g_wgrad_dp && peer_ready()) ? finish_dw<T>(dw, dw, (long long)M * N, 1, st) : 0;
+  }
   int splits, kps;
   size_t need = wgrad_ws<T>(p, &splits, &kps);
   if (ws_bytes < need || !ws) return fail("conv wgrad: workspace %zu < %zu bytes", ws_bytes, need);
@@ -1128,9 +1145,7 @@ int wgrad_t(const Plan& p, const T* dy, const T* x, T* dw, void* ws, size_t ws_b
     default: rc = launch_wgrad<T, typename Tiles<T>::WSmall>(wp, splits, st); break;
   }
   if (rc) return rc;
-  splitk_reduce<T><<<small_grid((long long)M * N), 256, 0, st>>>(partial, dw, (long long)M * N, splits);
-  MGB_LAUNCH_CHECK();
-  return 0;
+  return finish_dw<T>(partial, dw, (long long)M * N, splits, st);
 }
 
 }  // namespace
@@ -1214,6 +1229,15 @@ extern "C" int mgb_conv_wgrad_p(const mgb_conv_desc* d, const void* dy, const vo
     return tc_wgrad(p, (const float*)dy, (const float*)x, (float*)dw, dy_planes, x_planes, ws, ws_bytes,
                     as_stream(stream));
   return mgb_conv_wgrad(d, dy, x, dw, ws, ws_bytes, stream);
+}
+
+extern "C" int mgb_conv_wgrad_dp(const mgb_conv_desc* d, const void* dy, const void* x, void* dw,
+                                 const void* dy_planes, const void* x_planes, void* ws, size_t ws_bytes,
+                                 void* stream) {
+  g_wgrad_dp = true;
+  int rc = mgb_conv_wgrad_p(d, dy, x, dw, dy_planes, x_planes, ws, ws_bytes, stream);
+  g_wgrad_dp = false;
+  return rc;
 }
 
 extern "C" int mgb_conv_fwd(const mgb_conv_desc* d, const void* x, const void* w, void* y,

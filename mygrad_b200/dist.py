@@ -6,9 +6,17 @@ works on ``x[lo:hi]`` with a full replica of the filters; only parameter gradien
 (dW, broadcast biases) contract over the batch and need one sum all-reduce.  The
 result to match is the single-process reference on the full batch.
 
-``torch.distributed`` is used for rendezvous only (shipping the NCCL unique id and
-barriers); the all-reduce itself is ``mgb_allreduce_sum`` (ncclAllReduce on a side
-stream, ordered against the compute stream with events, so it can overlap dX).
+``torch.distributed`` is used for rendezvous only (shipping the NCCL unique id, the CUDA IPC
+handles and barriers).  Two collectives sit underneath:
+
+* ``mgb_peer_allreduce_sum`` / ``mgb_conv_wgrad_dp`` — our own one-kernel all-reduce over NVLink
+  peer memory (csrc/comm.cu): parameter gradients are a few hundred KB, i.e. pure latency, and the
+  dW one always follows the split-K reduction of the wgrad GEMM, so both run in ONE kernel
+  (``with dp.fused_wgrad(): loss.backward()``).  Results are summed in rank order in float64:
+  bit-identical on every rank.
+* ``mgb_allreduce_sum`` — ncclAllReduce on a side stream, ordered against the compute stream with
+  events, for buffers larger than a peer slot or when CUDA IPC is unavailable (``MGB_DP_PEER=0``
+  forces it).
 """
 from __future__ import annotations
 
@@ -21,7 +29,15 @@ import numpy as np
 from ._lib import check, lib
 from .device_array import DeviceArray, current_stream
 
-__all__ = ["shard_bounds", "scale_for_mean_loss", "DataParallel"]
+__all__ = ["shard_bounds", "scale_for_mean_loss", "DataParallel", "fused_dp"]
+
+_PEER_SLOT_BYTES = 8 << 20     # per-call capacity of the peer-memory all-reduce (dW of config 3 is 6.55 MB)
+_FUSED: Optional["DataParallel"] = None
+
+
+def fused_dp() -> Optional["DataParallel"]:
+    """the DataParallel whose ``fused_wgrad()`` context is active (ConvND.backward_var asks)"""
+    return _FUSED
 
 
 def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -52,6 +68,8 @@ class DataParallel:
         self._event = None
         self._ready = False
         self._buckets: dict = {}
+        self.peer_slot_bytes = 0          # > 0 once the peer-memory group is connected
+        self.peer_error: Optional[str] = None
 
     # -- setup ---------------------------------------------------------------------
     def init(self) -> "DataParallel":
@@ -74,10 +92,57 @@ class DataParallel:
             dist.broadcast_object_list(box, src=0)
             buf = (C.c_char * 128).from_buffer_copy(box[0])
             check(lib.mgb_comm_init_rank(buf, self.world_size, self.rank))
+            if os.environ.get("MGB_DP_PEER", "1") != "0":
+                self._init_peer(dist)
         self._ready = True
         return self
 
+    def _init_peer(self, dist) -> None:
+        """maps every rank's staging region into this process (CUDA IPC over NVLink); on any failure
+        the NCCL path stays in charge — all ranks decide together"""
+        handle = (C.c_char * 64)()
+        ok = lib.mgb_peer_create(self.rank, self.world_size, C.c_size_t(_PEER_SLOT_BYTES), handle) == 0
+        err = None if ok else lib.mgb_last_error().decode("utf-8", "replace")
+        boxes = [None] * self.world_size
+        dist.all_gather_object(boxes, (ok, bytes(handle.raw), err))
+        if all(b[0] for b in boxes):
+            blob = b"".join(b[1] for b in boxes)
+            ok = lib.mgb_peer_connect((C.c_char * len(blob)).from_buffer_copy(blob)) == 0
+            err = None if ok else lib.mgb_last_error().decode("utf-8", "replace")
+        else:
+            ok, err = False, next(b[2] for b in boxes if not b[0])
+        flags = [None] * self.world_size
+        dist.all_gather_object(flags, ok)
+        if all(flags):
+            n = C.c_size_t(0)
+            check(lib.mgb_peer_slot_bytes(C.byref(n)))
+            self.peer_slot_bytes = int(n.value)
+        else:
+            lib.mgb_peer_destroy()
+            self.peer_error = err or "a peer rank could not map the staging regions"
+
+    def fused_wgrad(self):
+        """context manager: conv filter gradients produced inside it are ALREADY summed over the ranks
+        (mgb_conv_wgrad_dp: split-K reduction and cross-rank sum in one kernel); pass them to
+        ``allreduce(..., summed=[...])`` so that they are only scaled, not reduced again"""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            global _FUSED
+            prev = _FUSED
+            _FUSED = self if (self.world_size > 1 and self.peer_slot_bytes > 0) else None
+            try:
+                yield self
+            finally:
+                _FUSED = prev
+
+        return ctx()
+
     def close(self) -> None:
+        if self.peer_slot_bytes:
+            lib.mgb_peer_destroy()
+            self.peer_slot_bytes = 0
         if self._ready and self.world_size > 1:
             lib.mgb_comm_destroy()
         if self._comm_stream is not None:
@@ -111,11 +176,26 @@ class DataParallel:
         check(lib.mgb_event_record(self._event, self._comm_stream))
         check(lib.mgb_stream_wait_event(C.c_void_p(current_stream()), self._event))
 
-    def allreduce(self, grads: Sequence[DeviceArray], scale: Optional[float] = None) -> None:
+    def _reduce_flat(self, flat: DeviceArray) -> None:
+        """one collective on one contiguous buffer: the peer-memory kernel when it fits, else NCCL"""
+        if 0 < flat.nbytes <= self.peer_slot_bytes:
+            check(lib.mgb_peer_allreduce_sum(C.c_void_p(flat.ptr), C.c_size_t(flat.size), flat.code,
+                                             C.c_void_p(current_stream())))
+        else:
+            self.allreduce_async([flat])
+            self.wait()
+
+    def allreduce(self, grads: Sequence[DeviceArray], scale: Optional[float] = None,
+                  summed: Sequence[DeviceArray] = ()) -> None:
         """sum all-reduce (then optional scaling) of every buffer.  Parameter gradients are small
         (C5: 0.26 MB in six tensors), so the cost is per-call latency: buffers of one dtype are
-        packed into a single bucket, reduced with ONE collective and unpacked."""
-        grads = list(grads)
+        packed into a single bucket, reduced with ONE collective and unpacked.  Buffers listed in
+        ``summed`` were already reduced by ``fused_wgrad()`` and are only scaled."""
+        done = {g.ptr for g in summed}
+        if scale is not None and scale != 1.0:
+            for g in summed:
+                g *= scale
+        grads = [g for g in grads if g.ptr not in done]
         if self.world_size == 1:
             if scale is not None and scale != 1.0:
                 for g in grads:
@@ -126,8 +206,7 @@ class DataParallel:
             by_dtype.setdefault(g.dtype.str, []).append(g)
         for group in by_dtype.values():
             if len(group) == 1:
-                self.allreduce_async(group)
-                self.wait()
+                self._reduce_flat(group[0])
                 if scale is not None and scale != 1.0:
                     group[0] *= scale
                 continue
@@ -141,8 +220,7 @@ class DataParallel:
                                          C.c_size_t(g.nbytes), stream))
                 off += g.size
             flat = DeviceArray((total,), group[0].dtype, _ptr=bucket.ptr, _base=bucket)
-            self.allreduce_async([flat])
-            self.wait()
+            self._reduce_flat(flat)
             if scale is not None and scale != 1.0:
                 flat *= scale
             off = 0

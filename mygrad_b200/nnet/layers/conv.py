@@ -160,9 +160,16 @@ class ConvND(Operation):
             # dy planes made by the dX pass of the same backward call are valid for this grad only
             cached = getattr(self, "_dy_planes", None)
             dyp = cached[1] if cached is not None and cached[0] == g.ptr else None
-            check(lib.mgb_conv_wgrad_p(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(xin.ptr),
-                                       C.c_void_p(dw.ptr), _ptr(dyp), _ptr(getattr(self, "_x_planes", None)),
-                                       C.c_void_p(ws.ptr if ws else 0), C.c_size_t(ws_bytes), stream))
+            # inside DataParallel.fused_wgrad() the split-K reduction also sums over the ranks
+            # (one kernel over NVLink peer memory); otherwise dW is this rank's own
+            from ...dist import fused_dp
+
+            dp = fused_dp()
+            wgrad = lib.mgb_conv_wgrad_dp if (dp is not None and dw.nbytes <= dp.peer_slot_bytes) \
+                else lib.mgb_conv_wgrad_p
+            check(wgrad(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(xin.ptr),
+                        C.c_void_p(dw.ptr), _ptr(dyp), _ptr(getattr(self, "_x_planes", None)),
+                        C.c_void_p(ws.ptr if ws else 0), C.c_size_t(ws_bytes), stream))
             self._dy_planes = None
             return dw
 
