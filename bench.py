@@ -260,7 +260,9 @@ def run_ours(args, cfg, name):
         with dp.fused_wgrad() as fused:     # dW: split-K reduction + cross-rank sum in one kernel
             o.backward()
         if world > 1:
-            dp.allreduce([wt.grad], summed=[wt.grad] if fused.peer_slot_bytes else [])
+            from mygrad_b200.dist import fused_dp   # noqa: F401  (the context has ended; ask the flag it used)
+            was_fused = fused.peer_slot_bytes > 0 and os.environ.get("MGB_DP_FUSED", "1") != "0"
+            dp.allreduce([wt.grad], summed=[wt.grad] if was_fused else [])
         return o, xt, wt
 
     def events():
@@ -288,12 +290,17 @@ def run_ours(args, cfg, name):
     # ---- device-resident throughput -----------------------------------------------------
     for _ in range(args.warmup):
         step(x_dev, w_dev)
-    barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    sampler.start()                       # spawns nvidia-smi: before the barrier, it takes tens of ms
+    barrier()
     n0, n1 = C.c_uint64(0), C.c_uint64(0)
-    lib.mgb_launch_count(C.byref(n0))
     e0, e1 = events()
+    # the host barrier leaves the ranks' STREAMS milliseconds apart; a one-element all-reduce queued right
+    # before the start event lines them up on the device, so no rank's clock runs while it waits for a
+    # late starter (the timed region itself is coupled by the dW exchange of every step)
+    align = mg.zeros((1,), np.float32)
+    dp.allreduce([align])
+    lib.mgb_launch_count(C.byref(n0))
     check(lib.mgb_event_record(e0, stream))
     for _ in range(args.steps):
         step(x_dev, w_dev)
@@ -302,6 +309,8 @@ def run_ours(args, cfg, name):
     barrier()
     lib.mgb_launch_count(C.byref(n1))
     clocks = sampler.stop()
+    if os.environ.get("MGB_BENCH_RANKTIMES"):
+        print(f"[rank {rank}] {total_ms / args.steps:.3f} ms/step on its own stream", file=sys.stderr, flush=True)
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps
     batch = cfg["x"][0]
@@ -553,7 +562,8 @@ def run_c5(args):
             loss.backward()
         if world > 1:   # the loss averages over the local batch: rescale so the sum is the global mean
             dp.allreduce([t.grad for t in p.values()], scale=scale_for_mean_loss(B, B * world),
-                         summed=[p["w1"].grad, p["w2"].grad] if fused.peer_slot_bytes else [])
+                         summed=[p["w1"].grad, p["w2"].grad]
+                         if (fused.peer_slot_bytes > 0 and os.environ.get("MGB_DP_FUSED", "1") != "0") else [])
         return loss, p
 
     def barrier():
@@ -565,13 +575,15 @@ def run_c5(args):
     stream = C.c_void_p(mg.current_stream())
     for _ in range(args.warmup):
         step()
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    barrier()
     n0, n1 = C.c_uint64(0), C.c_uint64(0)
-    lib.mgb_launch_count(C.byref(n0))
     e0, e1 = C.c_void_p(), C.c_void_p()
     check(lib.mgb_event_create(C.byref(e0))); check(lib.mgb_event_create(C.byref(e1)))
+    align = mg.zeros((1,), np.float32)      # line the ranks' streams up on the device (see run_ours)
+    dp.allreduce([align])
+    lib.mgb_launch_count(C.byref(n0))
     check(lib.mgb_event_record(e0, stream))
     for _ in range(args.steps):
         loss, _ = step()

@@ -101,9 +101,14 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-template <typename T>
-__device__ __forceinline__ T ld_peer(const T* p) {      // peer memory: never through a stale L1 line
-  return *reinterpret_cast<const volatile T*>(p);
+// 16-byte load from (possibly peer) memory at system scope: never served from a stale L1 line
+__device__ __forceinline__ float4 ld_peer16(const void* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
 }
 
 template <typename T>
@@ -111,9 +116,12 @@ __global__ void __launch_bounds__(256) peer_reduce_allreduce_kernel(const T* par
                                                                     long long n, T* out,
                                                                     PeerTable tab, int rank, int world,
                                                                     size_t slot_off, uint32_t epoch) {
+  constexpr int V = 16 / (int)sizeof(T);                  // elements per 16-byte pack
   const int c = blockIdx.x;
-  const long long per = (n + kPeerChunks - 1) / kPeerChunks;
-  const long long lo = (long long)c * per, hi = min(n, lo + per);
+  // chunks are whole packs, so that every remote access is one aligned 16-byte transaction
+  const long long packs = (n + V - 1) / V;
+  const long long per = (packs + kPeerChunks - 1) / kPeerChunks;
+  const long long lo = (long long)c * per * V, hi = min(n, lo + per * V);
   T* mine = reinterpret_cast<T*>(tab.base[rank] + kPeerFlagBytes + slot_off);
   // A: local split-K reduction into this rank's slot
   for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
@@ -121,27 +129,40 @@ __global__ void __launch_bounds__(256) peer_reduce_allreduce_kernel(const T* par
     for (int s = 0; s < splits; ++s) acc += (double)partial[(long long)s * n + i];
     mine[i] = (T)acc;
   }
-  __threadfence_system();
   __syncthreads();
-  // B: publish chunk c to every rank (own flag array included), then wait for every rank's chunk c
+  // B: publish chunk c to every rank (own flag array included), then wait for every rank's chunk c.
+  // The release is cumulative over the CTA's writes ordered before it by the barrier.
   if (threadIdx.x < world) {
     uint32_t* flag = reinterpret_cast<uint32_t*>(tab.base[threadIdx.x]) + rank * kPeerChunks + c;
     st_release_sys(flag, epoch);
-  }
-  if (threadIdx.x < world) {
-    const uint32_t* flag = reinterpret_cast<const uint32_t*>(tab.base[rank]) + threadIdx.x * kPeerChunks + c;
+    const uint32_t* seen = reinterpret_cast<const uint32_t*>(tab.base[rank]) + threadIdx.x * kPeerChunks + c;
     unsigned long long spin = 0;
-    while (ld_acquire_sys(flag) != epoch) {
+    while ((int32_t)(ld_acquire_sys(seen) - epoch) < 0) {     // epochs only grow
       if (++spin > (1ull << 31)) __trap();          // a peer that never arrives must not hang the GPU
     }
   }
   __syncthreads();
-  // C: sum the chunk over ranks in rank order
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    double acc = 0.0;
-    for (int r = 0; r < world; ++r)
-      acc += (double)ld_peer(reinterpret_cast<const T*>(tab.base[r] + kPeerFlagBytes + slot_off) + i);
-    out[i] = (T)acc;
+  // C: sum the chunk over ranks in rank order: all ranks' packs are requested first (independent
+  // 16-byte NVLink reads in flight), then added in float64
+  for (long long i = lo + (long long)threadIdx.x * V; i < hi; i += (long long)blockDim.x * V) {
+    float4 pack[kPeerMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kPeerMaxWorld; ++r)
+      if (r < world)
+        pack[r] = ld_peer16(reinterpret_cast<const T*>(tab.base[r] + kPeerFlagBytes + slot_off) + i);
+    double acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int r = 0; r < kPeerMaxWorld; ++r)
+      if (r < world) {
+        const T* e = reinterpret_cast<const T*>(&pack[r]);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += (double)e[k];
+      }
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+      if (i + k < hi) out[i + k] = (T)acc[k];
   }
 }
 

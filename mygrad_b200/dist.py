@@ -131,7 +131,8 @@ class DataParallel:
         def ctx():
             global _FUSED
             prev = _FUSED
-            _FUSED = self if (self.world_size > 1 and self.peer_slot_bytes > 0) else None
+            on = self.world_size > 1 and self.peer_slot_bytes > 0 and os.environ.get("MGB_DP_FUSED", "1") != "0"
+            _FUSED = self if on else None
             try:
                 yield self
             finally:
