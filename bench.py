@@ -260,8 +260,7 @@ def run_ours(args, cfg, name):
         with dp.fused_wgrad() as fused:     # dW: split-K reduction + cross-rank sum in one kernel
             o.backward()
         if world > 1:
-            from mygrad_b200.dist import fused_dp   # noqa: F401  (the context has ended; ask the flag it used)
-            was_fused = fused.peer_slot_bytes > 0 and os.environ.get("MGB_DP_FUSED", "1") != "0"
+            was_fused = fused.fuses(wt.grad.nbytes) and os.environ.get("MGB_DP_FUSED", "1") != "0"
             dp.allreduce([wt.grad], summed=[wt.grad] if was_fused else [])
         return o, xt, wt
 
@@ -473,6 +472,8 @@ def run_ours(args, cfg, name):
         cpu = {"value": b / times[0], "unit": "samples/s", "cores": host_threads(), "kind": kind,
                "sample": f"batch {b} of {batch} (same layer), one timed step after a 2-sample probe"}
 
+    collective = "peer" if (dp.fuses(int(np.prod(cfg["w"])) * geo["esz"])
+                            and os.environ.get("MGB_DP_FUSED", "1") != "0") else "nccl"
     if rank == 0:
         top = max(phases, key=lambda k: phases[k]["ms"])
         ph = phases[top]
@@ -504,7 +505,9 @@ def run_ours(args, cfg, name):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
             "config": {"workload": workload_name(name, cfg), "per_gpu_batch": batch,
-                       "parallelism": f"dp{world} (batch shards, dW all-reduce)" if world > 1 else "single GPU",
+                       "parallelism": (f"dp{world} (batch shards; dW summed by "
+                                       + ("the fused split-K + peer-memory kernel over NVLink" if collective == "peer"
+                                          else "ncclAllReduce") + ")") if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (x+y+dy > 126 MB), no flush between steps"
                              if geo["x_bytes"] + 2 * geo["y_bytes"] > 126e6 else "working set fits L2; not flushed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(n1.value - n0.value),
@@ -562,8 +565,8 @@ def run_c5(args):
             loss.backward()
         if world > 1:   # the loss averages over the local batch: rescale so the sum is the global mean
             dp.allreduce([t.grad for t in p.values()], scale=scale_for_mean_loss(B, B * world),
-                         summed=[p["w1"].grad, p["w2"].grad]
-                         if (fused.peer_slot_bytes > 0 and os.environ.get("MGB_DP_FUSED", "1") != "0") else [])
+                         summed=[g for g in (p["w1"].grad, p["w2"].grad)
+                                 if fused.fuses(g.nbytes) and os.environ.get("MGB_DP_FUSED", "1") != "0"])
         return loss, p
 
     def barrier():
@@ -624,7 +627,9 @@ def run_c5(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C5: x=(2048,3,32,32) -> conv3x3(32)+b+relu+pool2 -> conv3x3(64)+b+relu+pool2 -> "
                                    "dense 4096x10 -> softmax_crossentropy; Tensor.backward; x constant",
-                       "per_gpu_batch": B, "parallelism": f"dp{world}" if world > 1 else "single GPU"},
+                       "per_gpu_batch": B,
+                       "parallelism": (f"dp{world} (parameter grads: " + ("peer-memory kernels over NVLink"
+                                       if dp.peer_slot_bytes > 0 else "ncclAllReduce") + ")") if world > 1 else "single GPU"},
             "clocks": clocks, "gpu_launches": int(n1.value - n0.value), "loss": lv,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(px.nbytes + labels.nbytes), "d2h_bytes_per_step": 4},

@@ -32,6 +32,9 @@ from .device_array import DeviceArray, current_stream
 __all__ = ["shard_bounds", "scale_for_mean_loss", "DataParallel", "fused_dp"]
 
 _PEER_SLOT_BYTES = 8 << 20     # per-call capacity of the peer-memory all-reduce (dW of config 3 is 6.55 MB)
+# the one-shot kernel reads R-1 copies of the message: it wins while the message is latency-sized
+# (295 KB at 8 GPUs: 18 us vs 28 us for NCCL) and loses above ~1 MB (6.5 MB: 205 vs 65 us); MGB_DP_PEER_MAX overrides
+_PEER_MAX_BYTES = int(os.environ.get("MGB_DP_PEER_MAX", 1 << 20))
 _FUSED: Optional["DataParallel"] = None
 
 
@@ -121,10 +124,17 @@ class DataParallel:
             lib.mgb_peer_destroy()
             self.peer_error = err or "a peer rank could not map the staging regions"
 
+    def fuses(self, nbytes: int) -> bool:
+        """True when a gradient of `nbytes` goes through the peer-memory kernels (fused wgrad, bucket
+        all-reduce) rather than NCCL"""
+        return (self.world_size > 1 and 0 < nbytes <= min(self.peer_slot_bytes, _PEER_MAX_BYTES))
+
     def fused_wgrad(self):
         """context manager: conv filter gradients produced inside it are ALREADY summed over the ranks
         (mgb_conv_wgrad_dp: split-K reduction and cross-rank sum in one kernel); pass them to
-        ``allreduce(..., summed=[...])`` so that they are only scaled, not reduced again"""
+        ``allreduce(..., summed=[...])`` so that they are only scaled, not reduced again.  Filters larger
+        than the peer kernel's sweet spot (``fuses(nbytes)`` is False) keep the plain wgrad and must be
+        all-reduced as usual."""
         import contextlib
 
         @contextlib.contextmanager
@@ -179,7 +189,7 @@ class DataParallel:
 
     def _reduce_flat(self, flat: DeviceArray) -> None:
         """one collective on one contiguous buffer: the peer-memory kernel when it fits, else NCCL"""
-        if 0 < flat.nbytes <= self.peer_slot_bytes:
+        if self.fuses(flat.nbytes):
             check(lib.mgb_peer_allreduce_sum(C.c_void_p(flat.ptr), C.c_size_t(flat.size), flat.code,
                                              C.c_void_p(current_stream())))
         else:

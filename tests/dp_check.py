@@ -48,7 +48,7 @@ def conv_case(dp, dtype, n_total, fused: bool):
     if fused:
         with dp.fused_wgrad():
             out.backward()
-        assert dp.peer_slot_bytes > 0, f"peer group not connected: {dp.peer_error}"
+        assert dp.fuses(wt.grad.nbytes), f"peer group not connected: {dp.peer_error}"
     else:
         out.backward()
         dp.allreduce([wt.grad])

@@ -69,3 +69,76 @@ def test_two_rank_shards_match_full_batch():
     for r in results:
         np.testing.assert_allclose(r[5], dw, rtol=1e-10, atol=1e-10)              # summed dW on every rank
         np.testing.assert_allclose(r[6], dw / x.shape[0], rtol=1e-10, atol=1e-10)
+
+
+# ---- cross-rank batchnorm moments: the algebra of mgb_batchnorm_merge (csrc/batchnorm.cu) ----------
+
+def _merge_phases(moments, all_reduce):
+    """NumPy restatement of the three phases around two sum all-reduces (include/mgb.h):
+    moments = [mean, var, count] per channel of THIS rank; returns the full-batch [mean, var, count]"""
+    mean, var, n = moments
+    buf = np.concatenate([n, n * mean])                                   # phase 0
+    buf = all_reduce(buf)
+    gn, gsum = np.split(buf, 2)
+    gmean = np.where(gn > 0, gsum / np.maximum(gn, 1), 0.0)               # phase 1
+    m2 = var * n + n * (mean - gmean) ** 2
+    m2 = all_reduce(m2)
+    return gmean, np.where(gn > 0, m2 / np.maximum(gn, 1), 0.0), gn       # phase 2
+
+
+def _bn_worker(rank: int, world: int, port: int, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = np.random.default_rng(3).standard_normal((7, 5, 4, 3)) * 2 + 10
+        lo, hi = shard_bounds(x.shape[0], rank, world)
+        xs = x[lo:hi]
+        local = (xs.mean(axis=(0, 2, 3)), xs.var(axis=(0, 2, 3)), np.full(5, float(xs.size // 5)))
+
+        def all_reduce(a):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return t.numpy()
+
+        q.put((rank, *_merge_phases(local, all_reduce)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_batchnorm_moments_match_full_batch():
+    import torch.multiprocessing as mp
+
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bn_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=150) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x = np.random.default_rng(3).standard_normal((7, 5, 4, 3)) * 2 + 10
+    for _, mean, var, n in results:
+        np.testing.assert_allclose(mean, x.mean(axis=(0, 2, 3)), rtol=1e-13)
+        np.testing.assert_allclose(var, x.var(axis=(0, 2, 3)), rtol=1e-11)
+        np.testing.assert_array_equal(n, np.full(5, 7 * 12.0))
+
+
+def test_collective_choice_by_message_size():
+    """DataParallel.fuses(): peer-memory kernels for latency-sized messages only"""
+    from mygrad_b200.dist import DataParallel
+
+    dp = DataParallel(rank=0, world_size=8, local_rank=0)
+    assert not dp.fuses(1024)                       # no peer group connected -> NCCL
+    dp.peer_slot_bytes = 8 << 20
+    assert dp.fuses(128 * 64 * 9 * 4)               # dW of config 2 (295 KB)
+    assert not dp.fuses(256 * 128 * 25 * 8)         # dW of config 3 (6.5 MB): one-shot loses, NCCL
+    assert not dp.fuses(0)
+    assert not DataParallel(rank=0, world_size=1, local_rank=0).fuses(1024)
+    dp.peer_slot_bytes = 0                          # do not let close() touch a device
