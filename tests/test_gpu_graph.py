@@ -238,12 +238,13 @@ def test_host_pipeline_matches_single_pass():
         pipe.close()
 
 
-@pytest.mark.parametrize("path", ["tma", "cpasync", "mma"])
+@pytest.mark.parametrize("path", ["halo", "tma", "cpasync", "mma"])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_kernels_do_not_write_outside_their_outputs(path, dt, monkeypatch):
     """compute-sanitizer is closed on this pool, so out-of-bounds WRITES are caught with guard
     bands: every output sits between two sentinel regions inside one big allocation."""
-    monkeypatch.setenv("MGB_CONV_F32_PATH", path)
+    monkeypatch.setenv("MGB_CONV_F32_PATH", "tma" if path == "halo" else path)
+    monkeypatch.setenv("MGB_CONV_HALO", "1" if path == "halo" else "0")
     GUARD, SENT = 8192, -12345.0
     rng = np.random.default_rng(12)
     esz = np.dtype(dt).itemsize
