@@ -425,8 +425,15 @@ int tc_prep_planes(const float* src, float* hi, float* lo, long long n, long lon
                    long long spatial, int cpad, cudaStream_t st) {
   if (n * spatial == 0) return 0;
   if (n > 65535) return fail("conv (tcgen05 path): batch %lld > 65535 unsupported", n);
-  dim3 grid((unsigned)((spatial + 31) / 32), (unsigned)(cpad / 32), (unsigned)n);
-  tc::nchw_to_nhwc_split<<<grid, 256, 0, st>>>(src, hi, lo, (int)chans, spatial, cpad);
+  const bool wide = spatial % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                    !(getenv("MGB_PREP_V4") && getenv("MGB_PREP_V4")[0] == '0');
+  if (wide) {    // 16-byte loads and stores, 32 channels x 128 pixels per CTA
+    dim3 grid((unsigned)((spatial + 127) / 128), (unsigned)(cpad / 32), (unsigned)n);
+    tc::nchw_to_nhwc_split_v4<<<grid, 256, 0, st>>>(src, hi, lo, (int)chans, spatial, cpad);
+  } else {
+    dim3 grid((unsigned)((spatial + 31) / 32), (unsigned)(cpad / 32), (unsigned)n);
+    tc::nchw_to_nhwc_split<<<grid, 256, 0, st>>>(src, hi, lo, (int)chans, spatial, cpad);
+  }
   MGB_LAUNCH_CHECK();
   return 0;
 }

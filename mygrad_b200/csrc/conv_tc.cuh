@@ -589,6 +589,54 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_split(const float* __restric
   }
 }
 
+// the same transposition with 16-byte accesses on both sides (needs P % 4 == 0): a CTA moves
+// 32 channels x 128 pixels.  Loads are float4 along the pixels, stores float4 along the channels (8
+// lanes cover one pixel's 128-byte row of a plane); the shared tile is XOR-swizzled at float4
+// granularity — element (ch, px) lives at column ((px >> 2) ^ ((ch >> 2) & 7)) * 4 + (px & 3) — which
+// makes both the float4 writes (one channel per warp) and the scalar reads (8 channel quads x 4
+// consecutive pixels per warp) bank-conflict free without padding.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_split_v4(const float* __restrict__ x,
+                                                             float* __restrict__ hi,
+                                                             float* __restrict__ lo, int C, long long P,
+                                                             int cpad) {
+  __shared__ __align__(16) float tile[32][128];
+  const long long p0 = (long long)blockIdx.x * 128;
+  const int c0 = blockIdx.y * 32, n = blockIdx.z;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = threadIdx.x + 256 * i;
+    const int ch = idx >> 5, q = idx & 31;                  // one channel per warp, 32 float4 along the pixels
+    const int c = c0 + ch;
+    const long long pp = p0 + 4 * q;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C && pp < P) v = __ldg(reinterpret_cast<const float4*>(x + ((long long)n * C + c) * P + pp));
+    *reinterpret_cast<float4*>(&tile[ch][(q ^ ((ch >> 2) & 7)) * 4]) = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = threadIdx.x + 256 * i;
+    const int cq = idx & 7, px = idx >> 3;                  // 8 lanes = the 32 channels of one pixel
+    const long long pp = p0 + px;
+    if (pp < P) {
+      const int col = (((px >> 2) ^ cq) << 2) | (px & 3);
+      float4 h4, l4;
+      float* hp = reinterpret_cast<float*>(&h4);
+      float* lp = reinterpret_cast<float*>(&l4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t h, l;
+        split_tf32(tile[4 * cq + k][col], h, l);
+        hp[k] = __uint_as_float(h);
+        lp[k] = __uint_as_float(l);
+      }
+      const long long o = ((long long)n * P + pp) * cpad + c0 + 4 * cq;
+      *reinterpret_cast<float4*>(hi + o) = h4;
+      *reinterpret_cast<float4*>(lo + o) = l4;
+    }
+  }
+}
+
 // generic filter pack: out[row][tap_j][ch] = w[f][c][tap] with (row, ch) = (f, c) for fwd and
 // (c, f) for dgrad; rows/chs beyond the real extents are zero.  tap_list maps tap_j -> tap.
 struct PackArgs {
