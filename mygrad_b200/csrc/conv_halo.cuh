@@ -63,6 +63,14 @@ struct HaloParams {
   // uniform datapath (ULDC), so the descriptors the MMA thread builds from them stay in uniform registers
   uint32_t tapoff[kMaxInner];
   unsigned long long* prof;      // PROF instantiation only: per-CTA cycle counters of the MMA thread
+  // fused 2x2 / stride-2 max-pool over (row axis, column axis) in the epilogue: the
+  // accumulator tile never goes to HBM as y; each window's maximum and the position of its FIRST maximum
+  // in row-major window order (pooling.py:111, NaN counts as maximal) are written instead
+  int pool;                      // 0: store y;  1: store pooled + argmax (needs bnb <= 2, even P[ra], P[2])
+  float* pout;                   // [N][Nout][P[ra]/2][P[2]/2]
+  unsigned char* pidx;           // same shape: 2*(row & 1) + (col & 1) of the first maximum
+  long long p_sample_stride, p_chan_stride;
+  int pw;                        // pooled columns per row = P[2] / 2
 };
 
 __device__ __forceinline__ uint64_t smem_desc_k_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
@@ -335,11 +343,19 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
       gq[ra] = t.r0 + ir; gq[oa] = t.xo; gq[2] = t.c0 + ic;
       const bool pv = n < p.Nbatch && gq[ra] < p.P[ra] && gq[2] < p.P[2];
       long long rowoff = -1;
-      if (pv)
+      if (pv && !p.pool)
         rowoff = (long long)n * p.om.sample_stride +
                  (long long)(gq[0] * p.om.omul[0] + p.om.obase[0]) * p.om.os[0] +
                  (long long)(gq[1] * p.om.omul[1] + p.om.obase[1]) * p.om.os[1] +
                  (long long)(gq[2] * p.om.omul[2] + p.om.obase[2]) * p.om.os[2];
+      // pooled epilogue: the 2x2 window of this lane's pixel lives in four lanes of the same warp — the column
+      // partner is lane ^ 1, the row partner lane ^ rowbit (lanes are (row, sample, column) with 8 columns
+      // innermost; tiles start on even rows and columns).  The window's top-left lane stores.
+      const int rowbit = p.bnb == 1 ? 8 : 16;
+      const int wbase = lane & ~(1 | rowbit);
+      long long poff = -1;
+      if (p.pool && pv && lane == wbase)
+        poff = (long long)n * p.p_sample_stride + (long long)(gq[ra] >> 1) * p.pw + (gq[2] >> 1);
       tc::mbar_wait(tfull + buf, (uint32_t)((local / 2) & 1));
       tc::tc_fence_after();
       const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.acc_cols);
@@ -354,7 +370,26 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
           for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
 
         }
-        if (rowoff >= 0) {
+        if (p.pool) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            // window values in row-major order, then the reference's scan: first strict maximum, NaN wins once
+            const float x0 = __shfl_sync(0xffffffffu, __uint_as_float(v[j]), wbase);
+            const float x1 = __shfl_sync(0xffffffffu, __uint_as_float(v[j]), wbase | 1);
+            const float x2 = __shfl_sync(0xffffffffu, __uint_as_float(v[j]), wbase | rowbit);
+            const float x3 = __shfl_sync(0xffffffffu, __uint_as_float(v[j]), wbase | rowbit | 1);
+            float best = x0;
+            int bi = 0;
+            if (x1 > best || (x1 != x1 && best == best)) { best = x1; bi = 1; }
+            if (x2 > best || (x2 != x2 && best == best)) { best = x2; bi = 2; }
+            if (x3 > best || (x3 != x3 && best == best)) { best = x3; bi = 3; }
+            const int ch = ch0 + col + j;
+            if (poff >= 0 && ch < p.Nout) {
+              p.pout[poff + (long long)ch * p.p_chan_stride] = best;
+              p.pidx[poff + (long long)ch * p.p_chan_stride] = (unsigned char)bi;
+            }
+          }
+        } else if (rowoff >= 0) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             int ch = ch0 + col + j;

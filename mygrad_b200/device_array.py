@@ -9,6 +9,7 @@ Buffers are exchanged with other libraries through ``__cuda_array_interface__``
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -65,39 +66,75 @@ def dtype_code(dtype) -> int:
 # Exact-size block cache in front of the stream-ordered pool.  A training loop asks for
 # the same sizes every step; handing a freed block straight to the next request of that
 # size costs no driver call and never makes the pool grow or trim (which shows up as
-# multi-millisecond hiccups with GB-sized activations).  Re-use is safe in stream order:
-# every kernel of the previous owner was enqueued on the stream before the new owner's.
-_CACHE: dict = {}          # (stream, nbytes) -> [ptr, ...]
-_CACHE_LIMIT = int(64e9)   # bytes kept at most; beyond it blocks go back to the pool
+# multi-millisecond hiccups with GB-sized activations).  Re-use is safe in stream order
+# ONLY for blocks whose whole life was spent on the stream they were allocated on: every
+# kernel of the previous owner was then enqueued on that stream before the new owner's.
+# A block that was (or may have been) used on another stream — the current stream changed
+# while it was alive, or ``record_stream`` named a side stream — is not cached: it goes back
+# to the driver pool behind events that order the free after the work on those streams.
+_CACHE: dict = {}          # (device, stream, nbytes) -> [ptr, ...]
+_CACHE_LIMIT = int(float(os.environ.get("MGB_CACHE_LIMIT", 32e9)))   # bytes kept at most
 _cached_bytes = 0
+
+
+def _device() -> int:
+    d = C.c_int(0)
+    return d.value if lib.mgb_get_device(C.byref(d)) == 0 else 0
 
 
 def empty_cache() -> None:
     """returns every cached block to the driver's stream-ordered pool"""
     global _cached_bytes
-    for (stream, _), ptrs in list(_CACHE.items()):
+    cur = _device()
+    for (dev, stream, _), ptrs in list(_CACHE.items()):
+        if dev != cur:
+            lib.mgb_set_device(dev)
         for p in ptrs:
             lib.mgb_free_async(C.c_void_p(p), C.c_void_p(stream))
+        if dev != cur:
+            lib.mgb_set_device(cur)
     _CACHE.clear()
     _cached_bytes = 0
+
+
+def _order_after(stream: int, others) -> None:
+    """makes `stream` wait for everything queued so far on each stream of `others`"""
+    for o in others:
+        if o == stream:
+            continue
+        e = C.c_void_p()
+        if lib.mgb_event_create(C.byref(e)) != 0:
+            lib.mgb_stream_synchronize(C.c_void_p(o))      # no event to be had: fall back to a host wait
+            continue
+        lib.mgb_event_record(e, C.c_void_p(o))
+        lib.mgb_stream_wait_event(C.c_void_p(stream), e)
+        lib.mgb_event_destroy(e)
 
 
 class _Allocation:
     """owns one device allocation; recycled (stream-ordered) when the last view dies"""
 
-    __slots__ = ("ptr", "nbytes", "stream")
+    __slots__ = ("ptr", "nbytes", "stream", "device", "foreign")
 
     def __init__(self, nbytes: int):
+        global _cached_bytes
         self.nbytes = max(16, (nbytes + 511) // 512 * 512)
         self.stream = _stream
-        free = _CACHE.get((self.stream, self.nbytes))
+        self.device = _device()
+        self.foreign = None          # set of other streams this block was used on
+        free = _CACHE.get((self.device, self.stream, self.nbytes))
         if free:
-            global _cached_bytes
             self.ptr = free.pop()
             _cached_bytes -= self.nbytes
             return
         p = C.c_void_p()
-        check(lib.mgb_malloc_async(C.byref(p), C.c_size_t(self.nbytes), C.c_void_p(_stream)))
+        rc = lib.mgb_malloc_async(C.byref(p), C.c_size_t(self.nbytes), C.c_void_p(_stream))
+        if rc != 0 and _cached_bytes:
+            # the driver pool is exhausted while blocks sit idle in the cache: hand them back and retry once
+            empty_cache()
+            lib.mgb_device_synchronize()
+            rc = lib.mgb_malloc_async(C.byref(p), C.c_size_t(self.nbytes), C.c_void_p(_stream))
+        check(rc)
         self.ptr = int(p.value or 0)
 
     def __del__(self):
@@ -105,10 +142,14 @@ class _Allocation:
             global _cached_bytes
             if not self.ptr:
                 return
-            if _cached_bytes + self.nbytes <= _CACHE_LIMIT:
-                _CACHE.setdefault((self.stream, self.nbytes), []).append(self.ptr)
+            others = set(self.foreign or ())
+            if _stream != self.stream:
+                others.add(_stream)          # alive across a set_stream(): assume it was used there too
+            if not others and _cached_bytes + self.nbytes <= _CACHE_LIMIT and self.device == _device():
+                _CACHE.setdefault((self.device, self.stream, self.nbytes), []).append(self.ptr)
                 _cached_bytes += self.nbytes
             else:
+                _order_after(self.stream, others)
                 lib.mgb_free_async(C.c_void_p(self.ptr), C.c_void_p(self.stream))
             self.ptr = 0
         except Exception:  # interpreter shutdown
@@ -116,7 +157,7 @@ class _Allocation:
 
 
 class DeviceArray:
-    __slots__ = ("_alloc", "_keepalive", "ptr", "shape", "dtype", "base", "__weakref__")
+    __slots__ = ("_alloc", "_keepalive", "ptr", "shape", "dtype", "base", "reduced", "__weakref__")
 
     def __init__(self, shape: Sequence[int], dtype=np.float32, *, _alloc=None, _ptr=None,
                  _keepalive=None, _base=None):
@@ -128,6 +169,9 @@ class DeviceArray:
             raise TypeError(f"mygrad_b200 supports float32 and float64 device arrays, got {self.dtype}")
         self.base = _base
         self._keepalive = _keepalive
+        # True when the buffer already holds the SUM over all data-parallel ranks (fused wgrad,
+        # cross-rank batchnorm): DataParallel.allreduce then only scales it (dist.py)
+        self.reduced = bool(getattr(_base, "reduced", False)) if _base is not None else False
         if _ptr is not None:
             self._alloc = _alloc
             self.ptr = int(_ptr)
@@ -174,6 +218,16 @@ class DeviceArray:
             "version": 3,
             "stream": _stream if _stream else 1,  # 1 = legacy default stream in CAI v3
         }
+
+    def record_stream(self, stream) -> None:
+        """declares that work on `stream` (not the allocating stream) uses this buffer: its memory is
+        then released behind an event on that stream instead of being recycled in allocation-stream order"""
+        s = int(getattr(stream, "value", stream) or 0)
+        a = self._alloc if self._alloc is not None else getattr(self.base, "_alloc", None)
+        if a is not None and s != a.stream:
+            if a.foreign is None:
+                a.foreign = set()
+            a.foreign.add(s)
 
     # ---- construction / transfer -------------------------------------------------
     @classmethod
@@ -225,6 +279,7 @@ class DeviceArray:
         out = DeviceArray(self.shape, self.dtype)
         check(lib.mgb_copy_cast(self.code, self.code, C.c_size_t(self.size), C.c_void_p(self.ptr),
                                 C.c_void_p(out.ptr), C.c_void_p(_stream)))
+        out.reduced = self.reduced
         return out
 
     def astype(self, dtype, copy: bool = True) -> "DeviceArray":
@@ -234,6 +289,7 @@ class DeviceArray:
         out = DeviceArray(self.shape, dt)
         check(lib.mgb_copy_cast(self.code, out.code, C.c_size_t(self.size), C.c_void_p(self.ptr),
                                 C.c_void_p(out.ptr), C.c_void_p(_stream)))
+        out.reduced = self.reduced
         return out
 
     def __iadd__(self, other: "DeviceArray") -> "DeviceArray":
@@ -242,6 +298,11 @@ class DeviceArray:
             raise ValueError(f"in-place add needs equal shapes, got {self.shape} and {other.shape}")
         if other.dtype != self.dtype:
             other = other.astype(self.dtype)
+        if self.reduced != other.reduced:
+            raise RuntimeError(
+                "accumulating a gradient that is already summed over the data-parallel ranks with a rank-local "
+                "one: all-reduce the local contribution first (DataParallel.allreduce) or keep fused_wgrad() / "
+                "dp= off for parameters that also receive rank-local gradients")
         check(lib.mgb_axpy(self.code, C.c_size_t(self.size), C.c_void_p(other.ptr),
                            C.c_void_p(self.ptr), C.c_void_p(_stream)))
         return self
@@ -289,6 +350,7 @@ class DeviceArray:
         check(lib.mgb_reduce_broadcast(self.code, self.ndim, gs, len(var_shape), vs,
                                        C.c_void_p(self.ptr), C.c_void_p(out.ptr), 0,
                                        C.c_void_p(_stream)))
+        out.reduced = self.reduced
         return out
 
     def __repr__(self) -> str:

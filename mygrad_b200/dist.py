@@ -131,10 +131,11 @@ class DataParallel:
 
     def fused_wgrad(self):
         """context manager: conv filter gradients produced inside it are ALREADY summed over the ranks
-        (mgb_conv_wgrad_dp: split-K reduction and cross-rank sum in one kernel); pass them to
-        ``allreduce(..., summed=[...])`` so that they are only scaled, not reduced again.  Filters larger
-        than the peer kernel's sweet spot (``fuses(nbytes)`` is False) keep the plain wgrad and must be
-        all-reduced as usual."""
+        (mgb_conv_wgrad_dp: split-K reduction and cross-rank sum in one kernel).  Such buffers carry
+        ``DeviceArray.reduced = True`` (so do dgamma / dbeta of ``batchnorm(dp=...)``), and
+        ``allreduce`` only scales them — the caller passes every parameter gradient and never has to
+        re-derive which path a gradient took.  Filters larger than the peer kernel's sweet spot
+        (``fuses(nbytes)`` is False) keep the plain wgrad, stay rank-local and are all-reduced as usual."""
         import contextlib
 
         @contextlib.contextmanager
@@ -200,13 +201,17 @@ class DataParallel:
                   summed: Sequence[DeviceArray] = ()) -> None:
         """sum all-reduce (then optional scaling) of every buffer.  Parameter gradients are small
         (C5: 0.26 MB in six tensors), so the cost is per-call latency: buffers of one dtype are
-        packed into a single bucket, reduced with ONE collective and unpacked.  Buffers listed in
-        ``summed`` were already reduced by ``fused_wgrad()`` and are only scaled."""
-        done = {g.ptr for g in summed}
+        packed into a single bucket, reduced with ONE collective and unpacked.  Buffers whose
+        ``reduced`` flag is set (fused wgrad, cross-rank batchnorm) — or that are listed in ``summed`` —
+        already hold the sum over the ranks and are only scaled."""
+        grads = list(grads)
+        extra = {id(g) for g in summed}
+        pre = [g for g in grads if g.reduced or id(g) in extra]
+        pre += [g for g in summed if not any(g is h for h in grads)]
         if scale is not None and scale != 1.0:
-            for g in summed:
+            for g in pre:
                 g *= scale
-        grads = [g for g in grads if g.ptr not in done]
+        grads = [g for g in grads if not (g.reduced or id(g) in extra)]
         if self.world_size == 1:
             if scale is not None and scale != 1.0:
                 for g in grads:

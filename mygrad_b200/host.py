@@ -68,10 +68,17 @@ class HostLayerPipeline:
              dx: Optional[np.ndarray] = None, dw: Optional[np.ndarray] = None
              ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         compute = C.c_void_p(current_stream())
+        x, w = self._check_inputs(x, w)
         n = x.shape[0]
         nchunks = min(self.chunks, max(1, n))
         bounds = [shard_bounds(n, i, nchunks) for i in range(nchunks)]
         dt = x.dtype
+        # NumPy promotion of (x, w) is the dtype of y / out / dW (conv.py:97-99); x.grad keeps x's dtype (:118)
+        odt = np.result_type(x.dtype, w.dtype)
+        out_shape = self._out_shape(x.shape, w.shape)
+        out = self._check_result("out", out, out_shape, odt)
+        dx = self._check_result("dx", dx, x.shape, dt)
+        dw = self._check_result("dw", dw, w.shape, odt)
         # the filter bank goes first, on the compute stream
         wd = self._buffer("w", w.shape, w.dtype)
         check(lib.mgb_memcpy_h2d(C.c_void_p(wd.ptr), C.c_void_p(w.ctypes.data), C.c_size_t(w.nbytes), compute))
@@ -100,19 +107,19 @@ class HostLayerPipeline:
             else:
                 dw_total += wt.grad
             check(lib.mgb_event_record(self._event_for("comp", i), compute))
-            if out is None:
-                out = self._buffer("out", (n, *o.shape[1:]), dt, pinned=True)
-            if dx is None:
-                dx = self._buffer("dx", x.shape, dt, pinned=True)
+            if o.shape[1:] != out_shape[1:] or o.data.dtype != odt or xt.grad.dtype != dt:
+                raise RuntimeError(f"internal: result {o.shape} {o.data.dtype} does not match the planned "
+                                   f"{out_shape} {odt}")
             check(lib.mgb_stream_wait_event(self._d2h, self._event_for("comp", i)))
+            # o.data / xt.grad are read by the copy stream: `keep` holds them until BOTH streams have been
+            # synchronised below, so their blocks return to the allocation cache only after the copies are done
+            # (buffers handed to a side stream without such a fence need DeviceArray.record_stream)
             o_bytes = o.data.nbytes // max(1, m)
             check(lib.mgb_memcpy_d2h(C.c_void_p(out.ctypes.data + lo * o_bytes), C.c_void_p(o.data.ptr),
                                      C.c_size_t(m * o_bytes), self._d2h))
             check(lib.mgb_memcpy_d2h(C.c_void_p(dx.ctypes.data + lo * sample_bytes), C.c_void_p(xt.grad.ptr),
                                      C.c_size_t(m * sample_bytes), self._d2h))
             keep.append((o, xt, wt, y))
-        if dw is None:
-            dw = self._buffer("dw", w.shape, w.dtype, pinned=True)
         # dW is complete once the last chunk's accumulation has run: copy it on the compute stream
         check(lib.mgb_memcpy_d2h(C.c_void_p(dw.ctypes.data), C.c_void_p(dw_total.ptr), C.c_size_t(dw.nbytes),
                                  compute))
@@ -120,6 +127,48 @@ class HostLayerPipeline:
         check(lib.mgb_stream_synchronize(self._d2h))
         del keep
         return out, dx, dw
+
+    # ---- argument checking: raw pointers go to the copy engines, so nothing unchecked may reach them ----
+    @staticmethod
+    def _check_inputs(x: np.ndarray, w: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        x, w = np.asarray(x), np.asarray(w)
+        for name, a in (("x", x), ("w", w)):
+            if a.dtype not in (np.float32, np.float64):
+                raise TypeError(f"`{name}` must be float32 or float64, got {a.dtype}")
+        if x.ndim < 3 or x.ndim != w.ndim or x.shape[1] != w.shape[1]:
+            raise ValueError(f"`x` {x.shape} and `w` {w.shape} are not a (N, C, X...) batch and a (F, C, W...) filter bank")
+        # sliced / transposed views would upload the wrong bytes: make them contiguous (a copy, like the
+        # reference's own np.ascontiguousarray in sliding_window_view, nnet/layers/utils.py:198-199)
+        return np.ascontiguousarray(x), np.ascontiguousarray(w)
+
+    def _out_shape(self, x_shape, w_shape):
+        nd = len(x_shape) - 2
+        tup = lambda v: (int(v),) * nd if np.isscalar(v) else tuple(int(i) for i in v)
+        s, p, d = tup(self.conv_kw["stride"]), tup(self.conv_kw["padding"]), tup(self.conv_kw["dilation"])
+        g = []
+        for X, W, si, pi, di in zip(x_shape[2:], w_shape[2:], s, p, d):
+            num = X + 2 * pi - ((W - 1) * di + 1)
+            if num < 0 or num % si:
+                raise ValueError("Stride and kernel dimensions are incompatible")
+            g.append(num // si + 1)
+        if self.pool:
+            ps = tup(self.pool_stride) if not np.isscalar(self.pool_stride) else (int(self.pool_stride),) * len(self.pool)
+            k = len(g) - len(self.pool)
+            for i, (P, st) in enumerate(zip(self.pool, ps)):
+                num = g[k + i] - P
+                if num < 0 or num % st:
+                    raise ValueError("Stride and kernel dimensions are incompatible")
+                g[k + i] = num // st + 1
+        return (x_shape[0], w_shape[0], *g)
+
+    def _check_result(self, name: str, arr: Optional[np.ndarray], shape, dtype) -> np.ndarray:
+        if arr is None:
+            return self._buffer(name, shape, dtype, pinned=True)
+        if (not isinstance(arr, np.ndarray) or tuple(arr.shape) != tuple(shape) or arr.dtype != np.dtype(dtype)
+                or not arr.flags["C_CONTIGUOUS"] or not arr.flags["WRITEABLE"]):
+            raise ValueError(f"`{name}=` must be a writeable C-contiguous {np.dtype(dtype).name} array of shape "
+                             f"{tuple(shape)}; got {getattr(arr, 'dtype', type(arr))} {getattr(arr, 'shape', '')}")
+        return arr
 
     def close(self) -> None:
         for e in self._ev.values():

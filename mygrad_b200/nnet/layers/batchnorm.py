@@ -134,7 +134,11 @@ class BatchNorm(Operation):
         if not ((index == 1) or index == 2):
             raise IndexError(index)
         view = DeviceArray((c,), np.float64, _ptr=sums.ptr + row * c * 8, _base=sums)
-        return view.astype(dt)
+        out = view.astype(dt)
+        # with dp= the channel sums were all-reduced above: dgamma / dbeta already cover the global batch,
+        # and DataParallel.allreduce must not sum them again
+        out.reduced = self._dp is not None and self._dp.world_size > 1
+        return out
 
 
 def batchnorm(x, *, gamma=None, beta=None, eps: float, constant: Optional[bool] = None, dp=None) -> Tensor:

@@ -165,7 +165,9 @@ class ConvND(Operation):
             from ...dist import fused_dp
 
             dp = fused_dp()
-            wgrad = lib.mgb_conv_wgrad_dp if (dp is not None and dp.fuses(dw.nbytes)) else lib.mgb_conv_wgrad_p
+            fused = dp is not None and dp.fuses(dw.nbytes)
+            wgrad = lib.mgb_conv_wgrad_dp if fused else lib.mgb_conv_wgrad_p
+            dw.reduced = fused          # already the sum over the ranks: allreduce() will only scale it
             check(wgrad(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(xin.ptr),
                         C.c_void_p(dw.ptr), _ptr(dyp), _ptr(getattr(self, "_x_planes", None)),
                         C.c_void_p(ws.ptr if ws else 0), C.c_size_t(ws_bytes), stream))

@@ -36,6 +36,10 @@ def same_on_all_ranks(arr: np.ndarray, what: str):
     assert all(b == box[0] for b in box), f"{what}: ranks disagree bitwise"
 
 
+def world_gt1(dp) -> bool:
+    return dp.world_size > 1
+
+
 def conv_case(dp, dtype, n_total, fused: bool):
     rank, world = dp.rank, dp.world_size
     rng = np.random.default_rng(11)
@@ -49,6 +53,8 @@ def conv_case(dp, dtype, n_total, fused: bool):
         with dp.fused_wgrad():
             out.backward()
         assert dp.fuses(wt.grad.nbytes), f"peer group not connected: {dp.peer_error}"
+        assert wt.grad.reduced, "the fused wgrad must mark dW as already summed over the ranks"
+        dp.allreduce([wt.grad])      # must be a no-op for a reduced buffer (the library tracks it, not the caller)
     else:
         out.backward()
         dp.allreduce([wt.grad])
@@ -74,6 +80,9 @@ def batchnorm_case(dp, dtype):
     xt, gt, bt = Tensor(x[lo:hi]), Tensor(gamma), Tensor(beta)
     y = batchnorm(xt, gamma=gt, beta=bt, eps=1e-5, dp=dp)
     y.backward(g[lo:hi])
+    if world_gt1(dp):
+        assert gt.grad.reduced and bt.grad.reduced and not xt.grad.reduced
+    dp.allreduce([gt.grad, bt.grad])   # already global: must not be multiplied by world_size
     x64, g64 = x.astype(np.float64), g.astype(np.float64)
     want_y, _, _ = oc.batchnorm_fwd(x64, gamma, beta, 1e-5)
     want_dx, want_dg, want_db = oc.batchnorm_bwd(g64, x64, gamma, 1e-5)

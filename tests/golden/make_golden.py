@@ -119,6 +119,22 @@ def pool_inputs():
     return cases
 
 
+def ref_mean_pool(xt, pool, st):
+    """mean-pool composed ENTIRELY of the reference's own autodiff ops: strided basic-index slices of a
+    Tensor (one per window offset; tensor_base.py __getitem__), added and divided by the window size.
+    Its ``backward`` is therefore the reference's gradient of mean-pooling."""
+    import itertools
+
+    nd = len(pool)
+    G = [(X - P) // s + 1 for X, P, s in zip(xt.shape[xt.ndim - nd:], pool, st)]
+    acc = None
+    for offs in itertools.product(*[range(p) for p in pool]):
+        idx = (Ellipsis,) + tuple(slice(o, o + s * (g - 1) + 1, s) for o, s, g in zip(offs, st, G))
+        term = xt[idx]
+        acc = term if acc is None else acc + term
+    return acc / float(np.prod(pool))
+
+
 def run_pool_cases():
     out, manifest = {}, {}
     for i, (name, x, pool, stride) in enumerate(pool_inputs()):
@@ -136,6 +152,13 @@ def run_pool_cases():
         mean = np.ascontiguousarray(mean.transpose(axes[nd:] + axes[:nd])) if lead_nd else mean
         out[f"{name}/x"], out[f"{name}/g"] = x, g
         out[f"{name}/y"], out[f"{name}/dx"], out[f"{name}/mean"] = y.data, xt.grad, mean
+        if np.isfinite(x).all():      # gradient of mean-pooling from the reference's autodiff
+            xm = mg.Tensor(x)
+            ym = ref_mean_pool(xm, pool, st)
+            assert ym.shape == y.shape
+            np.testing.assert_allclose(ym.data, mean, rtol=1e-5 if x.dtype == np.float32 else 1e-12, atol=1e-6)
+            ym.backward(g)
+            out[f"{name}/mean_dx"] = xm.grad
         manifest[name] = {"pool": pool, "stride": stride}
     np.savez_compressed(HERE / "pool_cases.npz", manifest=json.dumps(manifest), **out)
     return len(manifest)

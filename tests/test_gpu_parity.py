@@ -111,15 +111,17 @@ def test_pool_vs_golden_bit_exact(name, pool_golden):
     np.testing.assert_array_equal(y.numpy(), c["y"], err_msg=name)
     assert x.grad.dtype == c["x"].dtype
     np.testing.assert_array_equal(x.grad.get(), c["dx"], err_msg=name + " dx")
-    # mean-pool: composed definition (parity unpinned by the reference)
+    # mean-pool: the reference has no such function.  Forward is pinned to the reference's
+    # sliding_window_view(...).mean(), backward to the gradient the reference's OWN autodiff gives for
+    # mean-pooling composed of its ops (strided Tensor slices, add, divide: make_golden.ref_mean_pool)
     xm = Tensor(c["x"])
     ym = mean_pool(xm, tuple(m["pool"]), m["stride"])
     rtol = 1e-10 if c["x"].dtype == np.float64 else 1e-5
     np.testing.assert_allclose(ym.numpy(), c["mean"], rtol=rtol, atol=rtol, equal_nan=True, err_msg=name)
     if np.isfinite(c["x"]).all():
         ym.backward(c["g"])
-        want = oc.mean_pool_bwd(c["g"], c["x"].shape, m["pool"], m["stride"])
-        np.testing.assert_allclose(xm.grad.get(), want, rtol=rtol, atol=rtol, err_msg=name)
+        assert xm.grad.dtype == c["x"].dtype
+        np.testing.assert_allclose(xm.grad.get(), c["mean_dx"], rtol=rtol, atol=rtol, err_msg=name + " mean dx")
 
 
 @pytest.mark.parametrize("name", GoldenFile("layer_cases.npz").names())
@@ -333,6 +335,22 @@ def test_full_size_spot_checks_and_properties(name):
     rtol = 1e-9 if dt == np.float64 else 2e-4
     assert abs(lhs - float((x.astype(np.float64) * dxh).sum())) <= rtol * max(1.0, abs(lhs)), name
     assert abs(lhs - float((w.astype(np.float64) * dwh).sum())) <= rtol * max(1.0, abs(lhs)), name
+
+    # (5) dW / dX of the FULL-SIZE layer against the oracle on a 2-sample slice (full spatial extent and channel
+    #     counts: the same kernels, tiles and split-K plan shape as the whole batch; (2) extends it by additivity).
+    #     The oracle is fed the dy the GPU routed (bit-exact on the GPU's own y, checked in (1)): in float32 a
+    #     near-tie inside a pooling window may legitimately resolve differently on y values that differ by 1e-6
+    x5, w5 = Tensor(x[:2]), Tensor(w)
+    y5 = conv_nd(x5, w5, stride=cfg["s"], padding=cfg["p"], dilation=cfg["d"])
+    (max_pool(y5, cfg["pool"], 2) if cfg["pool"] else y5).backward()
+    dy5 = y5.grad.get()
+    if cfg["pool"]:
+        np.testing.assert_array_equal(
+            dy5, oc.max_pool_bwd(np.ones((2, *out.shape[1:]), dt), y5.numpy(), cfg["pool"], 2).astype(dt))
+    dw_ref5 = oc.conv_dw(dy5, x[:2], w.shape, cfg["s"], cfg["p"], cfg["d"]).astype(dt)
+    dx_ref5 = oc.conv_dx(dy5, x[:2].shape, w, cfg["s"], cfg["p"], cfg["d"], dtype=dt)
+    assert_close(w5.grad.get(), dw_ref5, dt, err_msg=f"{name}: dW of a 2-sample slice vs the oracle")
+    assert_close(x5.grad.get(), dx_ref5, dt, err_msg=f"{name}: dX of a 2-sample slice vs the oracle")
 
     # (4) strided+dilated dX has exact zeros where no window lands (config 3)
     if name == "C3":

@@ -141,6 +141,9 @@ def test_pool_oracle_vs_golden_bit_exact(name, pool_golden, direct):
     with np.errstate(invalid="ignore"):
         np.testing.assert_allclose(oc.mean_pool_fwd(x, m["pool"], m["stride"]), c["mean"],
                                    rtol=rtol, atol=rtol, equal_nan=True)
+    if "mean_dx" in c:    # the oracle's mean-pool gradient against the reference's own autodiff (a7)
+        np.testing.assert_allclose(oc.mean_pool_bwd(g, x.shape, m["pool"], m["stride"]).astype(x.dtype),
+                                   c["mean_dx"], rtol=rtol, atol=rtol)
 
 
 def _layer_names():
