@@ -110,6 +110,24 @@ int mgb_pool_fwd(const mgb_pool_desc* d, const void* x, void* y, void* stream);
 int mgb_pool_bwd(const mgb_pool_desc* d, const void* dy, const void* x, void* dx,
                  void* stream);
 
+/* ---- conv_nd -> max_pool fused (opt-in, float32 tensor-core path) ----------
+ * The reference materialises y = conv_nd(x, w) (conv.py:102-103), re-reads it in MaxPoolND.__call__
+ * (pooling.py:93-98) and again in MaxPoolND.backward_var (pooling.py:109-149).  The fused pair keeps the
+ * conv accumulator tile on chip: the forward writes only the pooled values and, per window, the position
+ * (0..3, row-major) of its first maximum; the backward turns (dp, argmax) straight into the channels-last
+ * dy planes that mgb_conv_dgrad_p / mgb_conv_wgrad_p read.  Results are bit-identical to
+ * mgb_conv_fwd -> mgb_pool_fwd -> mgb_pool_bwd -> mgb_conv_make_planes.
+ * Supported: 2 spatial dims, conv stride 1, >= 16 input and output channels, pool (2,2) stride (2,2)
+ * over an even-sized conv output; *yes = 0 otherwise (callers then run the unfused entry points). */
+int mgb_conv_pool_supported(const mgb_conv_desc* d, const mgb_pool_desc* pd, int* yes);
+/* pooled: (N, F, G0/2, G1/2) float32; argmax: same shape, uint8; ws as for mgb_conv_fwd (which = 0) */
+int mgb_conv_pool_fwd(const mgb_conv_desc* d, const mgb_pool_desc* pd, const void* x, const void* w,
+                      void* pooled, void* argmax, const void* x_planes, void* ws, size_t ws_bytes,
+                      void* stream);
+/* dy_planes: mgb_conv_planes_bytes(d, 1) bytes, as made by mgb_conv_make_planes(d, 1, dy, ...) */
+int mgb_pool_bwd_planes(const mgb_conv_desc* d, const mgb_pool_desc* pd, const void* dp,
+                        const void* argmax, void* dy_planes, void* stream);
+
 /* ---- Tensor.backward reductions / element-wise --------------------------- */
 
 /* out = (accumulate ? out : 0) + sum of g over the broadcast axes:

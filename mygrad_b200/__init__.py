@@ -32,7 +32,7 @@ from .operation_base import Operation
 from .tensor_base import Tensor, asarray, tensor
 from . import nnet
 from .host import HostLayerPipeline
-from .nnet.layers import conv_nd, max_pool, mean_pool
+from .nnet.layers import conv_nd, conv_pool, max_pool, mean_pool
 from .math_ops import add, matmul, reshape
 from ._io import load, save
 
@@ -45,6 +45,6 @@ __all__ = [
     "DeviceArray", "asdevice", "empty", "zeros", "full", "full_like", "pinned_empty",
     "current_stream", "set_stream", "synchronize", "device_available", "empty_cache",
     "InvalidGradient", "InvalidBackprop", "DisconnectedView", "SkipGradient",
-    "nnet", "conv_nd", "max_pool", "mean_pool", "add", "matmul", "reshape", "save", "load", "HostLayerPipeline",
+    "nnet", "conv_nd", "max_pool", "mean_pool", "conv_pool", "add", "matmul", "reshape", "save", "load", "HostLayerPipeline",
     "lib", "LIB_PATH",
 ]

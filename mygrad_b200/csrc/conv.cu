@@ -512,16 +512,22 @@ struct TmaJob {                   // one fwd-like GEMM on channels-last planes
   long long nbatch;
   int cpad, ntaps, nout, bn, ny, rows;
   const TapBuild* tb = nullptr;   // per-axis tap lists (host copy) — the halo kernel addresses taps by axis
+  // fused 2x2/2 max-pool epilogue (halo kernel only): pooled values + argmax positions instead of `out`
+  int pool = 0;
+  float* pout = nullptr;
+  unsigned char* pidx = nullptr;
 };
 
 // ---- halo-reuse variant (conv_halo.cuh): returns 0 ok, 1 error, 2 not applicable -----------
 // MGB_CONV_HALO: unset = by cost model, "0" = never, "1" = whenever the geometry allows it
-int halo_launch(const TmaJob& j, cudaStream_t st) {
+int halo_launch(const TmaJob& j, cudaStream_t st, bool dry_run = false) {
   static_assert(halo::kMaxTap >= kMaxW, "tap table too small");
   EncodeTiledFn enc = tma_encoder();
   const char* eh = getenv("MGB_CONV_HALO");
-  if (!enc || !tma_enabled() || !j.tb || (eh && eh[0] == '0')) return 2;
-  const bool force = eh && eh[0] == '1';
+  if ((!enc && !dry_run) || !tma_enabled() || !j.tb || (eh && eh[0] == '0' && !j.pool)) return 2;
+  const bool force = (eh && eh[0] == '1') || j.pool;
+  // the pooled epilogue pairs rows inside one warp: 2-D grids with even extents, at most 2 samples per tile
+  if (j.pool && (j.P[0] != 1 || j.P[1] % 2 || j.P[2] % 2)) return 2;
   const TapBuild& tb = *j.tb;
   for (int i = 0; i < 3; ++i) if (j.pmul[i] != 1 || j.X[i] < 1 || j.P[i] < 1 || tb.cnt[i] < 1) return 2;
   if (tb.cnt[0] * tb.cnt[2] > halo::kMaxInner || tb.cnt[1] * tb.cnt[2] > halo::kMaxInner) return 2;
@@ -546,6 +552,7 @@ int halo_launch(const TmaJob& j, cudaStream_t st) {
     for (int bh = 16; bh >= 1; bh >>= 1) {
       const int bnb = 16 / bh;
       if (bh > next_pow2(j.P[ra]) || bnb > next_pow2(j.nbatch)) continue;
+      if (j.pool && bnb > 2) continue;
       const int hr = bh + maxd[ra] - mind[ra];
       if (hr > 256) continue;
       const long long tx = (long long)hr * bnb * hc * 128;
@@ -562,6 +569,7 @@ int halo_launch(const TmaJob& j, cudaStream_t st) {
     }
   }
   if (best < 0) return 2;
+  if (dry_run) return 0;
   if (!force) {
     // the plain TMA kernel re-loads a 2 x 16 KB A tile per tap but tiles with 128-pixel boxes of any shape
     int box[3], boxn;
@@ -600,6 +608,10 @@ int halo_launch(const TmaJob& j, cudaStream_t st) {
   const long long total = (long long)hp.tiles_r * hp.tiles_c * hp.tiles_n * j.P[oa] * j.ny;
   if (total > INT32_MAX) return 2;
   hp.total_tiles = (int)total;
+  hp.pool = j.pool; hp.pout = j.pout; hp.pidx = j.pidx;
+  hp.pw = j.P[2] / 2;
+  hp.p_chan_stride = (long long)(j.P[1] / 2) * (j.P[2] / 2);
+  hp.p_sample_stride = hp.p_chan_stride * j.nout;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   {
     // (Cpad, X_col, N, X_row, X_outer): the halo lands as [row][sample][column][128 B]
@@ -759,7 +771,7 @@ size_t tc_fwd_ws(const Plan& p) {
 // `planes` (optional): channels-last hi|lo planes made by mgb_conv_make_planes; when null
 // they are built in the workspace.
 int tc_fwd(const Plan& p, const float* x, const float* w, float* y, const void* planes, void* ws,
-           size_t ws_bytes, cudaStream_t st) {
+           size_t ws_bytes, cudaStream_t st, float* pout = nullptr, unsigned char* pidx = nullptr) {
   long long M = p.N * p.Gp;
   if (M * p.F == 0) return 0;
   TcPlanes P = tc_planes(0, p.N, p.C, p.Xp);
@@ -794,7 +806,9 @@ int tc_fwd(const Plan& p, const float* x, const float* w, float* y, const void* 
     j.om.os[2] = 1; j.om.os[1] = p.G[2]; j.om.os[0] = p.G[1] * p.G[2];
     j.nbatch = p.N; j.cpad = P.cpad; j.ntaps = L.ntaps; j.nout = (int)p.F; j.bn = L.bn; j.ny = L.ny;
     j.rows = L.rows; j.tb = &tb;
+    if (pout) { j.pool = 1; j.pout = pout; j.pidx = pidx; }
     int rc = halo_launch(j, st);
+    if (pout) return rc == 2 ? fail("conv_pool: the fused kernel does not apply to this geometry") : rc;
     if (rc == 2) rc = tma_launch(j, st);
     if (rc != 2) return rc;
   }
@@ -1054,6 +1068,89 @@ int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, const vo
   return finish_dw<float>(partial, dw, n_dw, L.splits, st);
 }
 
+// ---- conv -> max-pool fusion -----------------------------------------------
+
+// the fused forward applies to: float32 tensor-core eligible, 2 spatial dims, conv stride 1, pool (2,2)
+// stride (2,2) over exactly the conv output (even extents), and a halo tiling with <= 2 samples per tile
+bool conv_pool_applies(const Plan& p, const mgb_pool_desc* pd) {
+  if (!pd || pd->nd != 2 || pd->mode != 0 || pd->dtype != MGB_F32) return false;
+  if (!tc_eligible(p, 0) || !tc_eligible(p, 1) || !tc_eligible(p, 2)) return false;
+  if (p.X[0] != 1 || p.W[0] != 1 || p.G[0] != 1) return false;                  // 2 spatial dims (normalised to 3)
+  for (int i = 0; i < 3; ++i) if (p.S[i] != 1) return false;
+  for (int i = 0; i < 2; ++i)
+    if (pd->P[i] != 2 || pd->stride[i] != 2 || pd->X[i] != p.G[i + 1] || p.G[i + 1] % 2) return false;
+  if (pd->lead != p.N * p.F || p.N * p.F * p.Gp == 0) return false;
+  TapBuild tb;
+  for (int i = 0; i < 3; ++i) {
+    tb.cnt[i] = p.W[i]; tb.W[i] = p.W[i]; tb.X[i] = p.X[i];
+    for (int k = 0; k < p.W[i]; ++k) { tb.kidx[i][k] = (short)k; tb.delta[i][k] = (short)(k * p.D[i]); }
+  }
+  TcLayout L = tc_layout(0, p.C, p.F, (int)p.Wp);
+  TmaJob j;
+  for (int i = 0; i < 3; ++i) { j.P[i] = p.G[i]; j.pmul[i] = 1; j.base[i] = -p.Pd[i]; j.X[i] = p.X[i]; }
+  j.nbatch = p.N; j.cpad = L.cpad; j.ntaps = L.ntaps; j.nout = (int)p.F; j.bn = L.bn; j.ny = L.ny; j.rows = L.rows;
+  j.tb = &tb; j.pool = 1;
+  return halo_launch(j, 0, /*dry_run=*/true) == 0;
+}
+
+// dy of the fused layer, written straight as the channels-last TF32 hi / lo planes the dgrad and wgrad
+// kernels read (never as an NCHW tensor): dy[n][h][w][f] = dp[n][f][h/2][w/2] where the window's first
+// maximum sits, else 0 (pooling.py:109-149 for a tiling pool).  A CTA turns 32 channels x 64 pooled pixels
+// of dp / argmax (read along the pixels) into 256 output pixels x 128 B per plane (written along the channels).
+__global__ void __launch_bounds__(256) pool_bwd_planes_kernel(const float* __restrict__ dp,
+                                                              const unsigned char* __restrict__ am,
+                                                              float* __restrict__ hi, float* __restrict__ lo,
+                                                              int F, int PH, int PW, int cpad) {
+  __shared__ float val[32][65];
+  __shared__ unsigned char pos[32][68];
+  const int PP = PH * PW;
+  const int q0 = blockIdx.x * 64, c0 = blockIdx.y * 32, n = blockIdx.z;
+  {
+    const int ch = threadIdx.x >> 3, g = threadIdx.x & 7;       // 8 threads x 8 pooled pixels per channel
+    const int c = c0 + ch;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = q0 + g + 8 * i;                             // consecutive threads -> consecutive pixels
+      float v = 0.f;
+      unsigned char a = 255;
+      if (c < F && q < PP) {
+        const long long o = ((long long)n * F + c) * PP + q;
+        v = __ldg(dp + o);
+        a = __ldg(am + o);
+      }
+      val[ch][g + 8 * i] = v;
+      pos[ch][g + 8 * i] = a;
+    }
+  }
+  __syncthreads();
+  const int W = 2 * PW;
+  const int cq = threadIdx.x & 7;                               // 8 lanes = the 32 channels of one output pixel
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int item = (threadIdx.x >> 3) + 32 * it;              // 256 output pixels: (pooled pixel, position)
+    const int ql = item >> 2, ps = item & 3;
+    const int q = q0 + ql;
+    if (q < PP) {
+      const int ph = q / PW, pw = q - ph * PW;
+      const long long px = (long long)(2 * ph + (ps >> 1)) * W + 2 * pw + (ps & 1);
+      float4 h4, l4;
+      float* hp = reinterpret_cast<float*>(&h4);
+      float* lp = reinterpret_cast<float*>(&l4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float v = pos[4 * cq + k][ql] == ps ? val[4 * cq + k][ql] : 0.f;
+        uint32_t h, l;
+        split_tf32(v, h, l);
+        hp[k] = __uint_as_float(h);
+        lp[k] = __uint_as_float(l);
+      }
+      const long long o = ((long long)n * (4LL * PP) + px) * cpad + c0 + 4 * cq;
+      *reinterpret_cast<float4*>(hi + o) = h4;
+      *reinterpret_cast<float4*>(lo + o) = l4;
+    }
+  }
+}
+
 // ---- the three convolutions ------------------------------------------------------------
 
 template <typename T>
@@ -1278,4 +1375,43 @@ extern "C" int mgb_conv_wgrad(const mgb_conv_desc* d, const void* dy, const void
   if (p.dtype == MGB_F32)
     return wgrad_t<float>(p, (const float*)dy, (const float*)x, (float*)dw, ws, ws_bytes, as_stream(stream));
   return wgrad_t<double>(p, (const double*)dy, (const double*)x, (double*)dw, ws, ws_bytes, as_stream(stream));
+}
+
+// ---- conv -> max-pool fusion: C ABI ---------------------------------------------------------------
+
+extern "C" int mgb_conv_pool_supported(const mgb_conv_desc* d, const mgb_pool_desc* pd, int* yes) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (!yes) return fail("mgb_conv_pool_supported: null");
+  *yes = conv_pool_applies(p, pd) ? 1 : 0;
+  return 0;
+}
+
+extern "C" int mgb_conv_pool_fwd(const mgb_conv_desc* d, const mgb_pool_desc* pd, const void* x, const void* w,
+                                 void* pooled, void* argmax, const void* x_planes, void* ws, size_t ws_bytes,
+                                 void* stream) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (!conv_pool_applies(p, pd))
+    return fail("mgb_conv_pool_fwd: geometry not supported by the fused kernel (ask mgb_conv_pool_supported)");
+  if (!pooled || !argmax) return fail("mgb_conv_pool_fwd: null output");
+  return tc_fwd(p, (const float*)x, (const float*)w, nullptr, x_planes, ws, ws_bytes, as_stream(stream),
+                (float*)pooled, (unsigned char*)argmax);
+}
+
+extern "C" int mgb_pool_bwd_planes(const mgb_conv_desc* d, const mgb_pool_desc* pd, const void* dp,
+                                   const void* argmax, void* dy_planes, void* stream) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (!conv_pool_applies(p, pd)) return fail("mgb_pool_bwd_planes: geometry not supported by the fused kernels");
+  if (!dp || !argmax || !dy_planes) return fail("mgb_pool_bwd_planes: null buffer");
+  if (p.N > 65535) return fail("mgb_pool_bwd_planes: batch %lld > 65535 unsupported", p.N);
+  TcPlanes P = tc_planes(0, p.N, p.F, p.Gp);
+  const int PH = p.G[1] / 2, PW = p.G[2] / 2;
+  dim3 grid((unsigned)((PH * PW + 63) / 64), (unsigned)(P.cpad / 32), (unsigned)p.N);
+  pool_bwd_planes_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+      (const float*)dp, (const unsigned char*)argmax, (float*)((char*)dy_planes + P.hi_off),
+      (float*)((char*)dy_planes + P.lo_off), (int)p.F, PH, PW, P.cpad);
+  MGB_LAUNCH_CHECK();
+  return 0;
 }

@@ -125,6 +125,24 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
   __trap();
 }
 
+// maximum that propagates NaN (IEEE 754-2019 `maximum`): NaN if either input is NaN
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;\n" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+// `if (pred) { *a = v; *b = (uint8_t)k; }` as two predicated stores
+__device__ __forceinline__ void st_global_if(float* a, float v, unsigned char* b, int k, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.s32 q, %4, 0;\n\t"
+      "@q st.global.f32 [%0], %1;\n\t"
+      "@q st.global.u8 [%2], %3;\n\t}\n" ::"l"(a),
+      "f"(v), "l"(b), "r"(k), "r"((int)pred)
+      : "memory");
+}
+
 struct HaloTile {
   int n0, xo, r0, c0, y;
 };
@@ -350,11 +368,12 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
                  (long long)(gq[2] * p.om.omul[2] + p.om.obase[2]) * p.om.os[2];
       // pooled epilogue: the 2x2 window of this lane's pixel lives in four lanes of the same warp — the column
       // partner is lane ^ 1, the row partner lane ^ rowbit (lanes are (row, sample, column) with 8 columns
-      // innermost; tiles start on even rows and columns).  The window's top-left lane stores.
+      // innermost; tiles start on even rows and columns).
       const int rowbit = p.bnb == 1 ? 8 : 16;
       const int wbase = lane & ~(1 | rowbit);
+      const int wpos = ((lane & rowbit) ? 2 : 0) | (lane & 1);          // this lane's position in its window
       long long poff = -1;
-      if (p.pool && pv && lane == wbase)
+      if (p.pool && pv)
         poff = (long long)n * p.p_sample_stride + (long long)(gq[ra] >> 1) * p.pw + (gq[2] >> 1);
       tc::mbar_wait(tfull + buf, (uint32_t)((local / 2) & 1));
       tc::tc_fence_after();
@@ -371,23 +390,24 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
 
         }
         if (p.pool) {
+          // Per channel: the window maximum by two butterfly steps (max.NaN propagates NaNs), then every lane
+          // votes "my value is the maximum" (equal, or NaN when the maximum is NaN) and the FIRST voter in
+          // row-major window order is the reference's argmax (pooling.py:111: first strict maximum, the first
+          // NaN wins).  That lane stores ITS OWN value — bit-exact even for -0.0 / NaN payloads — and its
+          // position.  8 lanes of a warp store per channel: two 16-byte runs (4 pooled columns x 2 samples/rows).
+          long long o = poff + (long long)(ch0 + col) * p.p_chan_stride;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            // window values in row-major order, then the reference's scan: first strict maximum, NaN wins once
-            const float x0 = __shfl_sync(0xffffffffu, __uint_as_float(v[j]), wbase);
-            const float x1 = __shfl_sync(0xffffffffu, __uint_as_float(v[j]), wbase | 1);
-            const float x2 = __shfl_sync(0xffffffffu, __uint_as_float(v[j]), wbase | rowbit);
-            const float x3 = __shfl_sync(0xffffffffu, __uint_as_float(v[j]), wbase | rowbit | 1);
-            float best = x0;
-            int bi = 0;
-            if (x1 > best || (x1 != x1 && best == best)) { best = x1; bi = 1; }
-            if (x2 > best || (x2 != x2 && best == best)) { best = x2; bi = 2; }
-            if (x3 > best || (x3 != x3 && best == best)) { best = x3; bi = 3; }
-            const int ch = ch0 + col + j;
-            if (poff >= 0 && ch < p.Nout) {
-              p.pout[poff + (long long)ch * p.p_chan_stride] = best;
-              p.pidx[poff + (long long)ch * p.p_chan_stride] = (unsigned char)bi;
-            }
+            const float x = __uint_as_float(v[j]);
+            float m = fmax_nan(x, __shfl_xor_sync(0xffffffffu, x, 1));
+            m = fmax_nan(m, __shfl_xor_sync(0xffffffffu, m, rowbit));
+            const unsigned votes = __ballot_sync(0xffffffffu, x == m || x != x) >> wbase;
+            const unsigned nib = (votes & 3u) | ((votes >> (rowbit - 2)) & 12u);   // window order: bits 0..3
+            const int k = __ffs((int)nib) - 1;
+            // predicated, not branched: a divergent branch per channel (8 of 32 lanes store) costs far more
+            // than the two stores themselves
+            st_global_if(p.pout + o, x, p.pidx + o, k, poff >= 0 && k == wpos && ch0 + col + j < p.Nout);
+            o += p.p_chan_stride;
           }
         } else if (rowoff >= 0) {
 #pragma unroll

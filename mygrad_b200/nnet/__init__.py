@@ -2,7 +2,7 @@
 from . import activations, layers, losses
 from .activations import relu
 from .losses import softmax_crossentropy
-from .layers import batchnorm, conv_nd, max_pool, mean_pool
+from .layers import batchnorm, conv_nd, conv_pool, max_pool, mean_pool
 
-__all__ = ["layers", "activations", "losses", "conv_nd", "max_pool", "mean_pool", "batchnorm", "relu",
+__all__ = ["layers", "activations", "losses", "conv_nd", "max_pool", "mean_pool", "conv_pool", "batchnorm", "relu",
            "softmax_crossentropy"]

@@ -60,6 +60,20 @@ def _as_tuple(value, n: int, *, minimum: int, name: str) -> Tuple[int, ...]:
 
 class ConvND(Operation):
     def __call__(self, x: Tensor, w: Tensor, *, stride, padding=0, dilation=1) -> DeviceArray:
+        out_shape = self._plan(x, w, stride=stride, padding=padding, dilation=dilation)
+        xin, win = self._operands()
+        y = DeviceArray(out_shape, self._dtype)
+        ws, ws_bytes = self._workspace(0)
+        # operand cache of the tensor-core path: x planes are re-used by dW, dy planes by dX and dW
+        self._x_planes = self._make_planes(0, xin)
+        self._dy_planes = None
+        check(lib.mgb_conv_fwd_p(C.byref(self._desc), C.c_void_p(xin.ptr), C.c_void_p(win.ptr),
+                                 C.c_void_p(y.ptr), _ptr(self._x_planes), C.c_void_p(ws.ptr if ws else 0),
+                                 C.c_size_t(ws_bytes), C.c_void_p(current_stream())))
+        return y
+
+    def _plan(self, x: Tensor, w: Tensor, *, stride, padding=0, dilation=1) -> Tuple[int, ...]:
+        """validation, the op's public attributes and the C descriptor; returns the output shape"""
         self.variables = (x, w)
         xd, wd = x.data, w.data  # (N, C, X0, ...), (F, C, W0, ...)
 
@@ -107,17 +121,9 @@ class ConvND(Operation):
         for i in range(nd):
             d.X[i], d.W[i] = x_shape[i], w_shape[i]
             d.stride[i], d.pad[i], d.dil[i] = stride[i], padding[i], dilation[i]
-
-        xin, win = self._operands()
-        y = DeviceArray((xd.shape[0], wd.shape[0], *out_shape), self._dtype)
-        ws, ws_bytes = self._workspace(0)
-        # operand cache of the tensor-core path: x planes are re-used by dW, dy planes by dX and dW
-        self._x_planes = self._make_planes(0, xin)
+        self._x_planes = None
         self._dy_planes = None
-        check(lib.mgb_conv_fwd_p(C.byref(d), C.c_void_p(xin.ptr), C.c_void_p(win.ptr),
-                                 C.c_void_p(y.ptr), _ptr(self._x_planes), C.c_void_p(ws.ptr if ws else 0),
-                                 C.c_size_t(ws_bytes), C.c_void_p(current_stream())))
-        return y
+        return (xd.shape[0], wd.shape[0], *out_shape)
 
     def _make_planes(self, tensor: int, src: DeviceArray) -> Optional[DeviceArray]:
         n = C.c_size_t(0)
@@ -142,37 +148,45 @@ class ConvND(Operation):
         return _scratch(n.value), n.value
 
     def backward_var(self, grad: DeviceArray, index: int, **kwargs) -> DeviceArray:
-        x, w = (v.data for v in self.variables)
-        xin, win = self._operands()
         g = grad.astype(self._dtype, copy=False)
-        stream = C.c_void_p(current_stream())
         if index == 0:  # dX, shape of x, dtype of x (conv.py:118)
-            dx = DeviceArray(x.shape, self._dtype)
-            ws, ws_bytes = self._workspace(1)
             self._dy_planes = (g.ptr, self._make_planes(1, g))
-            check(lib.mgb_conv_dgrad_p(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(win.ptr),
-                                       C.c_void_p(dx.ptr), _ptr(self._dy_planes[1]),
-                                       C.c_void_p(ws.ptr if ws else 0), C.c_size_t(ws_bytes), stream))
-            return dx.astype(x.dtype, copy=False)
-        else:  # dW, shape of w
-            dw = DeviceArray(w.shape, self._dtype)
-            ws, ws_bytes = self._workspace(2)
-            # dy planes made by the dX pass of the same backward call are valid for this grad only
-            cached = getattr(self, "_dy_planes", None)
-            dyp = cached[1] if cached is not None and cached[0] == g.ptr else None
-            # inside DataParallel.fused_wgrad() the split-K reduction also sums over the ranks
-            # (one kernel over NVLink peer memory); otherwise dW is this rank's own
-            from ...dist import fused_dp
+            return self._dgrad(g, self._dy_planes[1])
+        # dW: dy planes made by the dX pass of the same backward call are valid for this grad only
+        cached = self._dy_planes
+        dyp = cached[1] if cached is not None and cached[0] == g.ptr else None
+        self._dy_planes = None
+        return self._wgrad(g, dyp)
 
-            dp = fused_dp()
-            fused = dp is not None and dp.fuses(dw.nbytes)
-            wgrad = lib.mgb_conv_wgrad_dp if fused else lib.mgb_conv_wgrad_p
-            dw.reduced = fused          # already the sum over the ranks: allreduce() will only scale it
-            check(wgrad(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(xin.ptr),
-                        C.c_void_p(dw.ptr), _ptr(dyp), _ptr(getattr(self, "_x_planes", None)),
-                        C.c_void_p(ws.ptr if ws else 0), C.c_size_t(ws_bytes), stream))
-            self._dy_planes = None
-            return dw
+    def _dgrad(self, g: Optional[DeviceArray], dy_planes: Optional[DeviceArray]) -> DeviceArray:
+        """dX from dy (`g`) and/or its channels-last planes (the fused conv_pool op passes planes only)"""
+        x = self.variables[0].data
+        _, win = self._operands()
+        dx = DeviceArray(x.shape, self._dtype)
+        ws, ws_bytes = self._workspace(1)
+        check(lib.mgb_conv_dgrad_p(C.byref(self._desc), _ptr(g), C.c_void_p(win.ptr),
+                                   C.c_void_p(dx.ptr), _ptr(dy_planes),
+                                   C.c_void_p(ws.ptr if ws else 0), C.c_size_t(ws_bytes),
+                                   C.c_void_p(current_stream())))
+        return dx.astype(x.dtype, copy=False)
+
+    def _wgrad(self, g: Optional[DeviceArray], dy_planes: Optional[DeviceArray]) -> DeviceArray:
+        w = self.variables[1].data
+        xin, _ = self._operands()
+        dw = DeviceArray(w.shape, self._dtype)
+        ws, ws_bytes = self._workspace(2)
+        # inside DataParallel.fused_wgrad() the split-K reduction also sums over the ranks
+        # (one kernel over NVLink peer memory); otherwise dW is this rank's own
+        from ...dist import fused_dp
+
+        dp = fused_dp()
+        fused = dp is not None and dp.fuses(dw.nbytes)
+        wgrad = lib.mgb_conv_wgrad_dp if fused else lib.mgb_conv_wgrad_p
+        dw.reduced = fused          # already the sum over the ranks: allreduce() will only scale it
+        check(wgrad(C.byref(self._desc), _ptr(g), C.c_void_p(xin.ptr),
+                    C.c_void_p(dw.ptr), _ptr(dy_planes), _ptr(self._x_planes),
+                    C.c_void_p(ws.ptr if ws else 0), C.c_size_t(ws_bytes), C.c_void_p(current_stream())))
+        return dw
 
 
 def conv_nd(

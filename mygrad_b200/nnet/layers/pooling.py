@@ -35,13 +35,23 @@ class MaxPoolND(Operation):
     def __call__(self, x: Tensor, pool, stride) -> DeviceArray:
         self.variables = (x,)
         xd = x.data
+        out_shape = self._plan(xd.shape, xd.dtype, pool, stride)
+        if len(self.pool) == 0:  # pooling over no axes is the identity
+            return xd.copy()
+        y = DeviceArray(out_shape, xd.dtype)
+        check(lib.mgb_pool_fwd(C.byref(self._desc), C.c_void_p(xd.ptr), C.c_void_p(y.ptr),
+                               C.c_void_p(current_stream())))
+        return y
+
+    def _plan(self, in_shape, dtype, pool, stride) -> Tuple[int, ...]:
+        """validation, the op's public attributes and the C descriptor; returns the output shape"""
 
         assert isinstance(pool, (tuple, list, np.ndarray)) and all(
             isinstance(i, Integral) and i >= 0 for i in pool
         )
         pool = tuple(int(i) for i in pool)
         assert all(i > 0 for i in pool)
-        assert xd.ndim >= len(pool), (
+        assert len(in_shape) >= len(pool), (
             "The number of pooled dimensions cannot exceed the dimensionality of the data."
         )
         num_pool = len(pool)
@@ -55,8 +65,8 @@ class MaxPoolND(Operation):
         self.pool = np.asarray(pool, dtype=int)
         self.stride = np.asarray(stride, dtype=int)
 
-        lead_shape = xd.shape[: xd.ndim - num_pool]
-        x_shape = xd.shape[xd.ndim - num_pool:]
+        lead_shape = tuple(in_shape[: len(in_shape) - num_pool])
+        x_shape = tuple(in_shape[len(in_shape) - num_pool:])
         out_shape = []
         ok = True
         for X, P, s in zip(x_shape, pool, stride):
@@ -76,7 +86,7 @@ class MaxPoolND(Operation):
             )
 
         d = PoolDesc()
-        d.dtype = xd.code
+        d.dtype = 0 if np.dtype(dtype) == np.float32 else 1
         d.nd = num_pool
         d.mode = self._mode
         lead = 1
@@ -86,13 +96,7 @@ class MaxPoolND(Operation):
         for i in range(num_pool):
             d.X[i], d.P[i], d.stride[i] = x_shape[i], pool[i], stride[i]
         self._desc = d
-
-        y = DeviceArray((*lead_shape, *out_shape), xd.dtype)
-        if num_pool == 0:  # pooling over no axes is the identity
-            return xd.copy()
-        check(lib.mgb_pool_fwd(C.byref(d), C.c_void_p(xd.ptr), C.c_void_p(y.ptr),
-                               C.c_void_p(current_stream())))
-        return y
+        return (*lead_shape, *out_shape)
 
     def backward_var(self, grad: DeviceArray, index: int, **kwargs) -> DeviceArray:
         xd = self.variables[index].data

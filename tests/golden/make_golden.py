@@ -172,6 +172,9 @@ LAYER_CASES = [
     ("layer_c3_like", (2, 4, 13, 13), (6, 4, 3, 3), 2, 0, 2, None, None, "f8"),
     ("layer_c4_like_f32", (2, 3, 6, 8, 8), (4, 3, 3, 3, 3), 1, 0, 1, (2, 2, 2), 2, "f4"),
     ("layer_overlap_pool", (2, 3, 9, 9), (4, 3, 3, 3), 1, 0, 1, (3, 3), 2, "f8"),
+    # >= 16 channels: the tcgen05 kernels, and the geometry of the fused conv_pool Operation
+    ("layer_tc_f32", (3, 16, 12, 12), (32, 16, 3, 3), 1, 1, 1, (2, 2), 2, "f4"),
+    ("layer_tc_dilated_f32", (2, 32, 10, 14), (16, 32, 3, 3), 1, 2, 2, (2, 2), 2, "f4"),
 ]
 
 
