@@ -116,7 +116,8 @@ int mgb_pool_bwd(const mgb_pool_desc* d, const void* dy, const void* x, void* dx
  * conv accumulator tile on chip: the forward writes only the pooled values and, per window, the position
  * (0..3, row-major) of its first maximum; the backward turns (dp, argmax) straight into the channels-last
  * dy planes that mgb_conv_dgrad_p / mgb_conv_wgrad_p read.  Results are bit-identical to
- * mgb_conv_fwd -> mgb_pool_fwd -> mgb_pool_bwd -> mgb_conv_make_planes.
+ * mgb_conv_fwd -> mgb_pool_fwd -> mgb_pool_bwd -> mgb_conv_make_planes when mgb_conv_fwd runs the same
+ * (halo) kernel, equal to rounding otherwise.
  * Supported: 2 spatial dims, conv stride 1, >= 16 input and output channels, pool (2,2) stride (2,2)
  * over an even-sized conv output; *yes = 0 otherwise (callers then run the unfused entry points). */
 int mgb_conv_pool_supported(const mgb_conv_desc* d, const mgb_pool_desc* pd, int* yes);

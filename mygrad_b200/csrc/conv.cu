@@ -10,6 +10,7 @@
 #include "conv_tc.cuh"
 #include "conv_tma.cuh"
 #include "conv_halo.cuh"
+#include "conv_halo2.cuh"
 
 namespace mgb {
 namespace conv {
@@ -533,7 +534,11 @@ int halo_launch(const TmaJob& j, cudaStream_t st, bool dry_run = false) {
   if (tb.cnt[0] * tb.cnt[2] > halo::kMaxInner || tb.cnt[1] * tb.cnt[2] > halo::kMaxInner) return 2;
   if (j.nbatch < 1) return 2;
   const bool ncat = j.bn % 8 == 0 && 2 * j.bn <= 256;
-  const int b_stage = 2 * j.bn * 128;
+  // CTA pairs (tcgen05 cta_group::2, conv_halo2.cuh): each SM stages, reads and fetches from L2 only half of
+  // the filter tile.  MGB_CONV_2CTA=0 keeps the single-CTA kernel, =1 is the default where it applies.
+  const char* e2 = getenv("MGB_CONV_2CTA");
+  const bool pair = !(e2 && e2[0] == '0') && ncat && j.bn % 32 == 0;
+  const int b_stage = pair ? j.bn * 128 : 2 * j.bn * 128;
   const long long smem_cap = 227 * 1024;
   int mind[3], maxd[3];
   for (int i = 0; i < 3; ++i) {
@@ -557,8 +562,9 @@ int halo_launch(const TmaJob& j, cudaStream_t st, bool dry_run = false) {
       if (hr > 256) continue;
       const long long tx = (long long)hr * bnb * hc * 128;
       const long long plane = (tx + 1023) / 1024 * 1024;
-      const long long left = smem_cap - (1024 + 256) - halo::AST * 2 * plane;
-      const int bst = (int)std::min<long long>(6, left / b_stage);
+      const long long left = smem_cap - (1024 + 512) - halo::AST * 2 * plane;
+      // filter stages arrive ~2000 clk after they are requested (L2 under load): the ring must cover that
+      const int bst = (int)std::min<long long>(pair ? 16 : 6, left / b_stage);
       if (bst < 2) continue;
       const long long tiles = (long long)((j.P[ra] + bh - 1) / bh) * ((j.nbatch + bnb - 1) / bnb) * j.P[oa] * tiles_c;
       // shared-memory bytes moved per tile: operand reads + filter writes per tap, halo writes per outer tap
@@ -605,9 +611,11 @@ int halo_launch(const TmaJob& j, cudaStream_t st, bool dry_run = false) {
   }
   hp.bn = j.bn; hp.ny = j.ny; hp.bst = b_bst;
   hp.ncat = ncat ? 1 : 0; hp.acc_cols = ncat ? 2 * j.bn : j.bn; hp.tmem_cols = pow2_cols(2 * hp.acc_cols);
-  const long long total = (long long)hp.tiles_r * hp.tiles_c * hp.tiles_n * j.P[oa] * j.ny;
-  if (total > INT32_MAX) return 2;
+  const long long mtiles = (long long)hp.tiles_r * hp.tiles_c * hp.tiles_n * j.P[oa];
+  const long long total = pair ? (mtiles + 1) / 2 * j.ny : mtiles * j.ny;
+  if (mtiles * j.ny > INT32_MAX) return 2;
   hp.total_tiles = (int)total;
+  hp.mtiles = (int)mtiles;
   hp.pool = j.pool; hp.pout = j.pout; hp.pidx = j.pidx;
   hp.pw = j.P[2] / 2;
   hp.p_chan_stride = (long long)(j.P[1] / 2) * (j.P[2] / 2);
@@ -634,7 +642,7 @@ int halo_launch(const TmaJob& j, cudaStream_t st, bool dry_run = false) {
     long long K = (long long)j.ntaps * j.cpad;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)j.rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    cuuint32_t box[2] = {32u, (cuuint32_t)j.bn};
+    cuuint32_t box[2] = {32u, (cuuint32_t)(pair ? j.bn / 2 : j.bn)};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r1 = enc(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)j.b_hi, dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -644,9 +652,52 @@ int halo_launch(const TmaJob& j, cudaStream_t st, bool dry_run = false) {
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return 2;
   }
+  hp.prof = nullptr;
+  hp.dbg = getenv("MGB_HALO2_DBG") ? atoi(getenv("MGB_HALO2_DBG")) : 0;
+  if (pair) {
+    size_t smem2 = halo::smem_bytes2(hp.a_plane, j.bn, hp.bst);
+    const bool prof = getenv("MGB_HALO_PROF") != nullptr;
+    static unsigned long long* prof_buf2 = nullptr;
+    if (prof) {
+      if (!prof_buf2) MGB_CUDA(cudaMalloc(&prof_buf2, 8 * 1024 * sizeof(unsigned long long)));
+      MGB_CUDA(cudaMemsetAsync(prof_buf2, 0, 8 * 1024 * sizeof(unsigned long long), st));
+      hp.prof = prof_buf2;
+    }
+    auto kern = prof ? halo::conv_halo2_kernel<true> : halo::conv_halo2_kernel<false>;
+    MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min<long long>(2 * total, sm_count() / 2 * 2));
+    cfg.blockDim = dim3(halo::THREADS);
+    cfg.dynamicSmemBytes = smem2;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MGB_CUDA(cudaLaunchKernelEx(&cfg, kern, hp, ma_hi, ma_lo, mb_hi, mb_lo));
+    count_launch();
+    if (prof) {
+      const int grid = (int)cfg.gridDim.x;
+      std::vector<unsigned long long> h(8 * 1024);
+      MGB_CUDA(cudaStreamSynchronize(st));
+      MGB_CUDA(cudaMemcpy(h.data(), prof_buf2, h.size() * 8, cudaMemcpyDeviceToHost));
+      const double stages = (double)total / (grid / 2) * hp.nchunk * tb.cnt[0] * tb.cnt[1] * tb.cnt[2];
+      double s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, peer[2] = {0, 0}, ns = 0;
+      for (int i = 0; i < grid; i += 2) ns += (double)h[4096 + i] / (grid / 2);
+      for (int i = 0; i < grid; i += 2) {
+        for (int k = 0; k < 8; ++k) s[k] += (double)h[8 * i + k] / (grid / 2);
+        peer[0] += (double)h[8 * (i + 1) + 6] / (grid / 2); peer[1] += (double)h[8 * (i + 1) + 7] / (grid / 2);
+      }
+      fprintf(stderr, "[halo2 prof] bn=%d pair tiles=%d bst=%d hr=%d hc=%d bnb=%d, per tap-stage: wait A %.0f, wait B %.0f, "
+              "wait tmem %.0f, umma issue %.0f, commit %.0f, total %.0f clk; B producer wait empty: leader %.0f, peer %.0f of %.0f\n",
+              j.bn, hp.total_tiles, hp.bst, hp.hr, hp.hc, hp.bnb, s[0] / stages, s[1] / stages, s[2] / stages, s[4] / stages,
+              s[5] / stages, s[3] / stages, s[6] / stages, peer[0] / stages, s[7] / stages);
+      fprintf(stderr, "[halo2 prof] MMA loop %.0f clk in %.1f us: SM clock %.0f MHz\n", s[3], ns / 1e3, s[3] / (ns / 1e3));
+    }
+    return 0;
+  }
   size_t smem = halo::smem_bytes(hp.a_plane, j.bn, hp.bst);
   int grid = (int)std::min<long long>(total, sm_count());
-  hp.prof = nullptr;
   if (getenv("MGB_HALO_PROF")) {
     // diagnostic build of the same kernel: where does the MMA thread spend its cycles?  (synchronous)
     static unsigned long long* prof_buf = nullptr;

@@ -59,6 +59,8 @@ struct HaloParams {
   int bst;                       // B stages
   int ncat, acc_cols, tmem_cols;
   int total_tiles;
+  int dbg;                       // timing experiments only (MGB_HALO2_DBG): 1 = MMA thread skips the B-stage wait
+  int mtiles;                    // pair kernel (conv_halo2.cuh): real M tiles; total_tiles then counts PAIR tiles
   // (halo byte offset >> 4) of each inner tap, row tap major: kernel parameters are read through the
   // uniform datapath (ULDC), so the descriptors the MMA thread builds from them stay in uniform registers
   uint32_t tapoff[kMaxInner];

@@ -12,7 +12,9 @@ them.  This opt-in Operation returns only the pooled tensor and keeps the rest o
 * backward — ``(dp, argmax)`` become the channels-last hi/lo planes of ``dy`` directly
   (``mgb_pool_bwd_planes``), which dX and dW then read; ``dy`` never exists as an NCHW tensor.
 
-Values, routing and both gradients are bit-identical to the unfused pair (tests/test_gpu_fused.py).
+Values, routing and both gradients are bit-identical to the unfused pair whenever ``conv_nd`` runs the
+same (halo) convolution kernel — its choice at layer sizes like BASELINE config 2 — and agree to rounding
+otherwise (tests/test_gpu_fused.py).
 Geometries the fused kernels do not cover (float64, strided convolutions, pools other than 2x2/2,
 fewer than 16 channels, 1-D / 3-D) run the same kernels as ``conv_nd`` + ``max_pool`` inside the op.
 """

@@ -30,3 +30,15 @@ for rep in range(2):
     print("--- pooled epilogue", file=sys.stderr, flush=True)
     check(lib.mgb_conv_pool_fwd(C.byref(cd), C.byref(pd), P(x), P(w), P(p), P(am), P(xp), P(ws), ws.nbytes, None))
     mg.synchronize()
+# dX of the same layer (N tile 64)
+dy = mg.asdevice(np.random.default_rng(2).standard_normal((N, 128, 56, 56), dtype=np.float32))
+dx = mg.empty((N, 64, 56, 56))
+check(lib.mgb_conv_workspace_bytes(C.byref(cd), 1, C.byref(n)))
+ws1 = mg.empty((n.value // 8 + 1,), np.float64)
+check(lib.mgb_conv_planes_bytes(C.byref(cd), 1, C.byref(n)))
+dyp = mg.empty((n.value // 8 + 1,), np.float64)
+check(lib.mgb_conv_make_planes(C.byref(cd), 1, C.c_void_p(dy.ptr), C.c_void_p(dyp.ptr), None))
+for rep in range(int(os.environ.get("PROF_REPS", 1))):
+    print("--- dgrad", file=sys.stderr, flush=True)
+    check(lib.mgb_conv_dgrad_p(C.byref(cd), P(dy), P(w), P(dx), P(dyp), P(ws1), ws1.nbytes, None))
+    mg.synchronize()

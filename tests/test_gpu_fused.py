@@ -47,8 +47,12 @@ FUSED_CASES = [
 
 
 @pytest.mark.parametrize("name,xs,ws,pad,dil", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
-def test_fused_equals_unfused_bitwise(name, xs, ws, pad, dil):
-    rng = np.random.default_rng(abs(hash(name)) % 2**31)
+def test_fused_equals_unfused_bitwise(name, xs, ws, pad, dil, monkeypatch):
+    # the fused forward always runs the halo kernel; the unfused conv_nd picks halo or the per-tap TMA kernel
+    # by a cost model (they group the 3xTF32 partial sums differently).  Pin the unfused side to the halo
+    # kernel — its default at layer sizes like C2 — so that "same kernel, same bits" is what is compared.
+    monkeypatch.setenv("MGB_CONV_HALO", "1")
+    rng = np.random.default_rng(sum(map(ord, name)))
     x = rng.standard_normal(xs).astype(np.float32)
     w = rng.standard_normal(ws).astype(np.float32)
     kw = dict(stride=1, padding=pad, dilation=dil)
@@ -70,7 +74,23 @@ def test_fused_equals_unfused_bitwise(name, xs, ws, pad, dil):
     assert_close(got[0], oc.max_pool_fwd(oc.conv_fwd(x, w, 1, pad, dil), (2, 2), 2), np.float32, err_msg=name)
 
 
-def test_fused_ties_and_nan_route_like_the_reference():
+def test_fused_ties_and_nan_route_like_the_reference(monkeypatch):
+    monkeypatch.setenv("MGB_CONV_HALO", "1")
+    _ties_and_nan()
+
+
+def test_fused_within_tolerance_of_unfused_whatever_kernel_it_picks():
+    rng = np.random.default_rng(21)
+    for xs, ws in (((2, 32, 10, 10), (160, 32, 3, 3)), ((3, 16, 6, 6), (16, 16, 3, 3))):
+        x, w = rng.standard_normal(xs).astype(np.float32), rng.standard_normal(ws).astype(np.float32)
+        g = rng.standard_normal((xs[0], ws[0], xs[2] // 2, xs[3] // 2)).astype(np.float32)
+        kw = dict(stride=1, padding=1, dilation=1)
+        want, got = _pair(x, w, kw, (2, 2), 2, g), _fused(x, w, kw, (2, 2), 2, g)
+        for nm, a, b in zip(("out", "dx", "dw"), got, want):
+            assert_close(a, b, np.float32, err_msg=nm)
+
+
+def _ties_and_nan():
     """integer data makes exact ties inside windows (first maximum in row-major order wins); a NaN in x makes
     whole neighbourhoods of y NaN (NaN counts as maximal, the first NaN wins)"""
     rng = np.random.default_rng(5)

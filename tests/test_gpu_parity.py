@@ -225,13 +225,13 @@ TC_CASES = [
 
 
 @pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "x".join(map(str, c[:3])) + f"_{len(c[3])}d")
-@pytest.mark.parametrize("path", ["halo", "tma", "tma2cta", "cpasync", "mma"])
+@pytest.mark.parametrize("path", ["halo", "halo2cta", "tma", "tma2cta", "cpasync", "mma"])
 def test_conv_f32_paths_vs_oracle(case, path, monkeypatch):
-    """every fp32 kernel family (tcgen05 fed by TMA with and without halo reuse, tcgen05 fed by
-    cp.async, mma.sync) against the oracle"""
-    monkeypatch.setenv("MGB_CONV_F32_PATH", "tma" if path in ("tma2cta", "halo") else path)
-    monkeypatch.setenv("MGB_CONV_2CTA", "1" if path == "tma2cta" else "0")   # cta_group::2 variant is opt-in
-    monkeypatch.setenv("MGB_CONV_HALO", "1" if path == "halo" else "0")      # "1": wherever the geometry allows
+    """every fp32 kernel family (tcgen05 fed by TMA with and without halo reuse, on one CTA and on CTA pairs
+    (cta_group::2), tcgen05 fed by cp.async, mma.sync) against the oracle"""
+    monkeypatch.setenv("MGB_CONV_F32_PATH", "tma" if path in ("tma2cta", "halo", "halo2cta") else path)
+    monkeypatch.setenv("MGB_CONV_2CTA", "1" if path in ("tma2cta", "halo2cta") else "0")
+    monkeypatch.setenv("MGB_CONV_HALO", "1" if path in ("halo", "halo2cta") else "0")   # "1": wherever the geometry allows
     N, C, F, X, W, s, p, d = case
     rng = np.random.default_rng(hash(case) % (2 ** 32))
     x = rng.standard_normal((N, C, *X)).astype(np.float32)
