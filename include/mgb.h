@@ -178,6 +178,17 @@ int mgb_matmul_skinny(int dtype, int which, int64_t n, int64_t d, int64_t m, con
 /* dst[i] = (*scalar) * src[i], scalar on the device — `grad * self.back` (softmax_crossentropy.py:50) */
 int mgb_scale_by(int dtype, size_t n, const void* scalar, const void* src, void* dst, void* stream);
 
+/* Einstein summation  out[o] = sum_s prod_k op_k[...]  over strided operands: o runs over `nout` output
+ * labels, s over `nsum` summed labels; every operand and the output are addressed through one ELEMENT
+ * stride per label (0 = the operand does not vary with that label; the sum of several axis strides = a
+ * repeated label, i.e. a diagonal).  Stride tables are row-major [operand][label].  Up to 8 operands and
+ * 16 + 16 labels; products and sums in float64.  The output must be zero-filled by the caller when its
+ * strides do not cover it (gradients written along a diagonal).
+ * replaces np.einsum as called by EinSum.__call__ / backward_var (src/mygrad/linalg/ops.py:79-243) */
+int mgb_einsum(int dtype, int nops, const void* const* ops, int nout, const int64_t* out_size,
+               const int64_t* out_stride, const int64_t* op_out_stride, int nsum, const int64_t* sum_size,
+               const int64_t* op_sum_stride, void* out, void* stream);
+
 /* dst (G..., lead, W...) = windows of src (lead, X...) over its nd (1..3) trailing axes,
  * G = (X - ((W-1)*dil + 1)) / step + 1 — sliding_window_view (src/mygrad/nnet/layers/utils.py:7-228),
  * materialised because device arrays carry no strides.  The conv kernels never call this. */

@@ -82,6 +82,7 @@ EXPORTS = {
     "mgb_softmax_xent": (_i, [_i, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "mgb_scale_by": (_i, [_i, _sz, _vp, _vp, _vp, _vp]),
     "mgb_matmul_skinny": (_i, [_i, _i, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
+    "mgb_einsum": (_i, [_i, _i, C.POINTER(_vp), _i, _i64p, _i64p, _i64p, _i, _i64p, _i64p, _vp, _vp]),
     "mgb_window_gather": (_i, [_i, _i, C.c_int64, _i64p, _i64p, _i64p, _i64p, _vp, _vp, _vp]),
     "mgb_batchnorm_workspace_bytes": (_i, [C.c_int64, C.c_int64, C.POINTER(_sz)]),
     "mgb_batchnorm_stats": (_i, [_i, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _sz, _vp]),

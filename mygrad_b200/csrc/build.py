@@ -18,7 +18,7 @@ PKG = HERE.parent
 LIB = PKG / "libmgb200.so"
 OBJ_DIR = HERE / "build"
 
-SOURCES = ["runtime.cu", "pool.cu", "elementwise.cu", "conv.cu", "nnops.cu", "batchnorm.cu", "comm.cu", "peaks.cu"]
+SOURCES = ["runtime.cu", "pool.cu", "elementwise.cu", "conv.cu", "nnops.cu", "batchnorm.cu", "comm.cu", "peaks.cu", "einsum.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

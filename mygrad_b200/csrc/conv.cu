@@ -995,7 +995,10 @@ int wgrad_tma_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const fl
   const bool flat = p.X[0] == 1 && p.G[0] == 1;              // <= 2 spatial dims
   const bool mergeable = !flat && p.Pd[0] == 0;               // 3-D with an unpadded outer axis
   wp.blocked = ((flat || mergeable) && L.nbpc % L.cblocks == 0) ? 1 : 0;
-  wp.pix = wp.blocked ? 32 : tma::WG_PIX;
+  // pixels per pipeline stage: 32 (2 stages) by default; MGB_WGRAD_PIX=16 -> 16-pixel stages, 5 of them
+  const char* epx = getenv("MGB_WGRAD_PIX");
+  const int blocked_pix = (epx && atoi(epx) == 16) ? 16 : 32;
+  wp.pix = wp.blocked ? blocked_pix : tma::WG_PIX;
   if (wp.blocked && !flat) {
     if (!choose_box(p.G, p.S, p.N, wp.box, &wp.boxn, wp.pix, true)) { wp.blocked = 0; wp.pix = tma::WG_PIX; }
   }
@@ -1047,7 +1050,34 @@ int wgrad_tma_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const fl
   wp.boxes_total = (int)boxes; wp.boxes_per_split = (int)per;
   wp.tmem_cols = pow2_cols(L.nbpc * 32);
   dim3 grid(L.mt, L.nt, splits);
-  if (wp.pix == 32) {
+  wp.prof = nullptr;
+  static unsigned long long* wprof = nullptr;
+  const bool prof = getenv("MGB_WGRAD_PROF") != nullptr;
+  if (prof) {
+    if (!wprof) MGB_CUDA(cudaMalloc(&wprof, 4096 * 4 * sizeof(unsigned long long)));
+    MGB_CUDA(cudaMemsetAsync(wprof, 0, 4096 * 4 * sizeof(unsigned long long), st));
+    if ((long long)L.mt * L.nt * splits <= 4096) wp.prof = wprof;
+  }
+  struct ProfPrint {
+    bool on; unsigned long long* buf; int n, pix, nbpc; cudaStream_t st;
+    ~ProfPrint() {
+      if (!on) return;
+      std::vector<unsigned long long> h((size_t)n * 4);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h.data(), buf, h.size() * 8, cudaMemcpyDeviceToHost);
+      double wf = 0, tot = 0, S = 0;
+      for (int i = 0; i < n; ++i) { wf += (double)h[4 * i]; tot += (double)h[4 * i + 1]; S += (double)h[4 * i + 2]; }
+      fprintf(stderr, "[wgrad prof] %d CTAs, pix %d, nbpc %d: per stage wait full %.0f, total %.0f clk (tensor floor %.0f)\n",
+              n, pix, nbpc, wf / S, tot / S, (pix / 8) * 3.0 * nbpc * 16.0);
+    }
+  } prof_print{wp.prof != nullptr, wprof, (int)(L.mt * L.nt * splits), wp.pix, L.nbpc, st};
+  if (wp.pix == 16 && wp.blocked) {
+    constexpr int STAGES = 5;
+    size_t smem = tma::wgrad_smem_bytes(L.nbpc, STAGES, wp.pix);
+    MGB_CUDA(cudaFuncSetAttribute(tma::wgrad_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    tma::wgrad_tma_kernel<STAGES><<<grid, tma::THREADS, smem, st>>>(wp, mdy_hi, mdy_lo, mx_hi, mx_lo);
+  } else if (wp.pix == 32) {
     constexpr int STAGES = 2;
     size_t smem = tma::wgrad_smem_bytes(L.nbpc, STAGES, wp.pix);
     MGB_CUDA(cudaFuncSetAttribute(tma::wgrad_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -517,6 +517,7 @@ struct WgradTmaParams {
   // all c-blocks of one tap of x.  Small boxes are what limits TMA here, not bytes.
   int blocked;
   int X0, G0;                              // outermost spatial extents of x and dy (for the merged axis)
+  unsigned long long* prof;                // diagnostics (MGB_WGRAD_PROF): per-CTA cycle counters of the MMA thread
 };
 
 inline size_t wgrad_smem_bytes(int nbpc, int stages, int pix) {
@@ -615,9 +616,13 @@ wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant
     if (tc::elect_one()) {
       // ===== MMA issuer: A and B MN-major, N = nvalid*32 =====
       const uint32_t idesc = tc::idesc_tf32(nvalid * 32) | (1u << 15) | (1u << 16);
+      long long wf = 0, t0 = 0, c0 = 0;
+      if (p.prof) t0 = clock64();
       for (int s = 0; s < S; ++s) {
         const int stage = s % STAGES;
+        if (p.prof) c0 = clock64();
         tc::mbar_wait(full_bar + stage, (uint32_t)((s / STAGES) & 1));
+        if (p.prof) wf += clock64() - c0;
         tc::tc_fence_after();
         const uint32_t a_hi = smem_base + stage * stage_bytes;
         const uint32_t a_lo = a_hi + a_plane;
@@ -636,6 +641,12 @@ wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant
         tc::umma_commit(empty_bar + stage);
       }
       if (S > 0) tc::umma_commit(accum_bar);
+      if (p.prof) {
+        const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        p.prof[cta * 4 + 0] = (unsigned long long)wf;
+        p.prof[cta * 4 + 1] = (unsigned long long)(clock64() - t0);
+        p.prof[cta * 4 + 2] = (unsigned long long)S;
+      }
     }
   } else {
     // ===== epilogue: lane = f, columns = (block, channel) -> partial[f][c][tap] =====

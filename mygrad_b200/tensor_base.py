@@ -30,6 +30,22 @@ from .operation_base import Operation
 __all__ = ["Tensor", "tensor", "asarray"]
 
 
+def _broadcast_to(g: DeviceArray, shape: Tuple[int, ...]) -> DeviceArray:
+    """materialised np.broadcast_to on the device: zeros(shape) + g"""
+    import ctypes as C
+
+    from ._lib import check, lib
+    from .device_array import current_stream, zeros
+
+    nd = len(shape)
+    i64 = lambda v: (C.c_int64 * max(1, len(v)))(*[int(i) for i in v])
+    base, out = zeros(shape, g.dtype), DeviceArray(shape, g.dtype)
+    gs = (1,) * (nd - g.ndim) + tuple(g.shape)
+    check(lib.mgb_add_broadcast(out.code, nd, i64(shape), i64(shape), i64(gs), C.c_void_p(base.ptr),
+                                C.c_void_p(g.ptr), C.c_void_p(out.ptr), C.c_void_p(current_stream())))
+    return out
+
+
 def asarray(x) -> DeviceArray:
     """the DeviceArray behind a Tensor, or `x` moved/viewed onto the device"""
     return x.data if isinstance(x, Tensor) else asdevice(x)
@@ -202,15 +218,24 @@ class Tensor:
                                 f"shape.\n`grad` must be broadcast-compatible with "
                                 f"`tensor.shape={self.shape}`\nGot `grad.shape={host.shape}`"
                             )
-                    g = asdevice(np.ascontiguousarray(host))
+                    # (np.ascontiguousarray would turn a 0-d gradient into a 1-d one)
+                    g = asdevice(np.array(host, dtype=self.dtype, order="C", copy=True))
             if g.dtype != self.dtype:
                 g = g.astype(self.dtype)
             if g.shape != self.shape:
-                raise ValueError(
-                    f"`tensor.backward(grad)` was passed a gradient with an incompatible shape.\n"
-                    f"`grad` must be broadcast-compatible with `tensor.shape={self.shape}`\n"
-                    f"Got `grad.shape={g.shape}`"
-                )
+                # a device gradient of broadcast-compatible shape is broadcast like a host one
+                # (tensor_base.py:1311-1330 uses np.broadcast_to): zeros(shape) + g on the device
+                try:
+                    ok = np.broadcast_shapes(g.shape, self.shape) == self.shape
+                except ValueError:
+                    ok = False
+                if not ok:
+                    raise ValueError(
+                        f"`tensor.backward(grad)` was passed a gradient with an incompatible shape.\n"
+                        f"`grad` must be broadcast-compatible with `tensor.shape={self.shape}`\n"
+                        f"Got `grad.shape={g.shape}`"
+                    )
+                g = _broadcast_to(g, self.shape)
             seed = g
         else:
             seed = full_like(self.data, 1.0)

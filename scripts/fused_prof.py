@@ -42,3 +42,11 @@ for rep in range(int(os.environ.get("PROF_REPS", 1))):
     print("--- dgrad", file=sys.stderr, flush=True)
     check(lib.mgb_conv_dgrad_p(C.byref(cd), P(dy), P(w), P(dx), P(dyp), P(ws1), ws1.nbytes, None))
     mg.synchronize()
+# dW of the same layer
+dw = mg.empty((128, 64, 3, 3))
+check(lib.mgb_conv_workspace_bytes(C.byref(cd), 2, C.byref(n)))
+ws2 = mg.empty((n.value // 8 + 1,), np.float64)
+for rep in range(3):
+    print("--- wgrad", file=sys.stderr, flush=True)
+    check(lib.mgb_conv_wgrad_p(C.byref(cd), P(dy), P(x), P(dw), P(dyp), P(xp), P(ws2), ws2.nbytes, None))
+    mg.synchronize()

@@ -194,6 +194,57 @@ def run_layer_cases():
     return len(manifest)
 
 
+# ---- einsum through the reference's EinSum (linalg/ops.py:79-243) ------------------------------
+EINSUM_CASES = [
+    # name, subscripts, operand shapes, dtype, same_tensor (operand indices that are ONE tensor)
+    ("matmul", "ij,jk->ik", [(4, 5), (5, 3)], "f8", None),
+    ("matmul_implicit", "ij,jk", [(3, 4), (4, 6)], "f8", None),
+    ("transpose_implicit", "ba", [(2, 3)], "f8", None),
+    ("trace", "ii", [(5, 5)], "f8", None),
+    ("diag", "ii->i", [(4, 4)], "f8", None),
+    ("docstring_ijk_k", "ijk,k->ji", [(2, 3, 4), (4,)], "f8", None),
+    ("sum_without_partner", "ijk,jk->k", [(3, 2, 4), (2, 4)], "f8", None),
+    ("full_sum", "ij->", [(3, 4)], "f8", None),
+    ("inner", "i,i", [(7,), (7,)], "f8", None),
+    ("outer", "i,j->ij", [(3,), (4,)], "f8", None),
+    ("three_operands", "ij,jk,kl->il", [(2, 3), (3, 4), (4, 5)], "f8", None),
+    ("tensor_product", "ijk,jil->kl", [(3, 4, 5), (4, 3, 2)], "f8", None),
+    ("trace_repeat_kept", "iji->ij", [(3, 4, 3)], "f8", None),
+    ("double_trace", "ijkji,k->jk", [(2, 3, 4, 3, 2), (4,)], "f8", None),
+    ("ellipsis_matmul", "...ij,...jk->...ik", [(5, 1, 2, 3), (4, 3, 2)], "f8", None),
+    ("ellipsis_trace", "i...i", [(3, 2, 3)], "f8", None),
+    ("ellipsis_diag", "...ii->...i", [(2, 3, 3)], "f8", None),
+    ("ellipsis_middle", "ij...,jk...->ik...", [(2, 3, 4), (3, 5, 4)], "f8", None),
+    ("same_tensor_sq_norm", "...,...->", [(3, 4), (3, 4)], "f8", (0, 1)),
+    ("same_tensor_two_labels", "ij,ji->", [(3, 3), (3, 3)], "f8", (0, 1)),
+    ("same_tensor_matmul", "ij,jk->ik", [(3, 3), (3, 3)], "f8", (0, 1)),
+    ("scaled", ",ij->ij", [(), (2, 3)], "f8", None),
+    ("f32_matmul", "ij,jk->ik", [(8, 16), (16, 4)], "f4", None),
+    ("f32_batched", "bij,bjk->bik", [(3, 4, 5), (3, 5, 2)], "f4", None),
+    ("upper_case_labels", "Ab,bC->AC", [(2, 3), (3, 4)], "f8", None),
+]
+
+
+def run_einsum_cases():
+    out, manifest = {}, {}
+    for i, (name, subs, shapes, dt, same) in enumerate(EINSUM_CASES):
+        arrs = [rng_arr(900 + 10 * i + k, s, dt) for k, s in enumerate(shapes)]
+        ts = [mg.Tensor(a) for a in arrs]
+        if same:
+            for k in same[1:]:
+                ts[k] = ts[same[0]]
+                arrs[k] = arrs[same[0]]
+        y = mg.einsum(subs, *ts)
+        g = np.random.default_rng(950 + i).standard_normal(y.shape).astype(dt)
+        y.backward(g)
+        out[f"{name}/y"], out[f"{name}/g"] = np.asarray(y.data), g
+        for k, (a, t) in enumerate(zip(arrs, ts)):
+            out[f"{name}/op{k}"], out[f"{name}/grad{k}"] = a, t.grad
+        manifest[name] = {"subscripts": subs, "nops": len(shapes), "same": same}
+    np.savez_compressed(HERE / "einsum_cases.npz", manifest=json.dumps(manifest), **out)
+    return len(manifest)
+
+
 # ---- Operation.backward semantics: accumulation, un-broadcast, dtype casting -------------
 def run_graph_cases():
     out = {}
@@ -340,6 +391,10 @@ def run_io_and_window_cases():
     return len(manifest)
 
 
+if __name__ == "__main__" and "--einsum-only" in sys.argv:
+    print("einsum cases:", run_einsum_cases())
+    sys.exit(0)
+
 if __name__ == "__main__":
     print("reference:", mg.__file__)
     print("io / window cases:", run_io_and_window_cases())
@@ -349,5 +404,6 @@ if __name__ == "__main__":
     print("layer cases:", run_layer_cases())
     print("graph cases:", run_graph_cases())
     print("cnn cases:", run_cnn_case())
+    print("einsum cases:", run_einsum_cases())
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")

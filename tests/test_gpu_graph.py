@@ -307,3 +307,85 @@ def test_kernels_do_not_write_outside_their_outputs(path, dt, monkeypatch):
         check(lib.mgb_pool_bwd(C.byref(pd), C.c_void_p(gd.ptr), C.c_void_p(xd.ptr), C.c_void_p(dx_ptr), None))
         np.testing.assert_array_equal(check_guard(dx_big, xh.size, "pool bwd").reshape(shape),
                                       oc.max_pool_bwd(gh, xh, pool, stride).astype(dt))
+
+
+def test_device_gradients_broadcast_and_zero_d_seeds():
+    """`backward(grad)` broadcasts device gradients like host ones (tensor_base.py:1311-1330), and a 0-d
+    terminal keeps a 0-d gradient"""
+    rng = np.random.default_rng(4)
+    xh, wh = rng.standard_normal((2, 2, 6, 6)), rng.standard_normal((3, 2, 3, 3))
+    x, w = Tensor(xh), Tensor(wh)
+    y = conv_nd(x, w, stride=1)
+    y.backward(mg.asdevice(np.array(3.0)))                       # 0-d device gradient
+    np.testing.assert_array_equal(y.grad.get(), np.full(y.shape, 3.0))
+    y = conv_nd(x, w, stride=1)
+    row = rng.standard_normal((y.shape[-1],))
+    y.backward(mg.asdevice(row))                                  # trailing-axis device gradient
+    np.testing.assert_array_equal(y.grad.get(), np.broadcast_to(row, y.shape))
+    y = conv_nd(x, w, stride=1)
+    with pytest.raises(ValueError):
+        y.backward(mg.asdevice(np.ones((5,))))
+    y.clear_graph()
+    s = mg.einsum("ij,ij->", Tensor(xh[0, 0]), Tensor(xh[0, 1]))
+    assert s.shape == ()
+    s.backward(2.0)
+    assert s.grad.shape == ()
+
+
+def test_host_pipeline_validates_its_arguments():
+    """raw pointers go to the copy engines: strided views are made contiguous, mixed dtypes size the
+    outputs by the promoted dtype, and wrong out= / dx= / dw= buffers are rejected"""
+    rng = np.random.default_rng(2)
+    big = rng.standard_normal((6, 16, 12, 24)).astype(np.float32)
+    xv = big[::2, :, :, ::2]                                     # non-contiguous view, shape (3, 16, 12, 12)
+    w64 = rng.standard_normal((16, 16, 3, 3))                    # float64 filters with float32 x
+    pipe = mg.HostLayerPipeline(stride=1, padding=1, pool=(2, 2), pool_stride=2, chunks=2)
+    out, dx, dw = pipe.step(xv, w64)
+    assert (out.dtype, dx.dtype, dw.dtype) == (np.float64, np.float32, np.float64)
+    want = oc.layer_step(np.ascontiguousarray(xv), w64, stride=1, padding=1, dilation=1, pool=(2, 2), pool_stride=2)
+    assert_close(out, want[0], np.float32); assert_close(dx, want[1], np.float32); assert_close(dw, want[2], np.float32)
+    x32 = np.ascontiguousarray(xv)
+    for bad in (dict(out=np.empty((3, 16, 6, 6), np.float32)),            # dtype of the promoted output is f64
+                dict(dx=np.empty((3, 16, 12, 11), np.float32)),           # shape
+                dict(dw=np.empty((16, 16, 3, 3, 2), np.float64)[..., 0]),  # not contiguous
+                dict(out="nope")):
+        with pytest.raises(ValueError):
+            pipe.step(x32, w64, **bad)
+    with pytest.raises(TypeError):
+        pipe.step(x32.astype(np.int32), w64)
+    with pytest.raises(ValueError):
+        pipe.step(x32[:, :8], w64)                                # channel mismatch
+    own = dict(out=np.empty((3, 16, 6, 6), np.float64), dx=np.empty(x32.shape, np.float32),
+               dw=np.empty(w64.shape, np.float64))
+    o2, dx2, dw2 = pipe.step(x32, w64, **own)
+    assert o2 is own["out"] and dx2 is own["dx"] and dw2 is own["dw"]
+    np.testing.assert_array_equal(o2, out)
+    pipe.close()
+
+
+def test_allocation_cache_respects_streams_and_devices():
+    """a block that lived across a set_stream() is not recycled in allocation-stream order, and
+    empty_cache() followed by new allocations still works"""
+    import ctypes as C
+
+    a = mg.empty((1 << 16,), np.float32)
+    ptr_a = a.ptr
+    del a
+    b = mg.empty((1 << 16,), np.float32)
+    assert b.ptr == ptr_a                                     # same stream, same size: recycled
+    s = C.c_void_p()
+    assert lib.mgb_stream_create(C.byref(s)) == 0
+    try:
+        mg.set_stream(s.value)
+        b.fill(1.0)                                           # used on the other stream
+        del b                                                 # freed behind an event, not cached for stream 0
+        mg.set_stream(None)
+        c = mg.empty((1 << 16,), np.float32)
+        c.fill(2.0)
+        assert float(c.get()[0]) == 2.0
+    finally:
+        mg.set_stream(None)
+        lib.mgb_stream_destroy(s)
+    mg.empty_cache()
+    d = mg.full((1 << 16,), 3.0, np.float32)
+    assert float(d.get()[-1]) == 3.0
