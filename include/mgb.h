@@ -279,6 +279,10 @@ int mgb_peer_create(int rank, int world_size, size_t slot_bytes, void* ipc_handl
 int mgb_peer_connect(const void* handles);
 int mgb_peer_destroy(void);
 int mgb_peer_slot_bytes(size_t* bytes);
+/* *timed_out_call = ordinal of the first peer all-reduce that gave up waiting for a rank (0 = none; the
+ * kernels wait at most 30 s and then raise this flag instead of hanging or trapping), *waited_for_rank =
+ * the rank it was waiting for.  Once set, every later peer call fails with the same report. */
+int mgb_peer_status(int* timed_out_call, int* waited_for_rank);
 int mgb_peer_allreduce_sum(void* buf, size_t n, int dtype, void* stream);
 int mgb_conv_wgrad_dp(const mgb_conv_desc* d, const void* dy, const void* x, void* dw,
                       const void* dy_planes, const void* x_planes, void* ws, size_t ws_bytes,

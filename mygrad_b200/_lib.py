@@ -125,6 +125,7 @@ EXPORTS = {
     "mgb_peer_connect": (_i, [_vp]),
     "mgb_peer_destroy": (_i, []),
     "mgb_peer_slot_bytes": (_i, [C.POINTER(_sz)]),
+    "mgb_peer_status": (_i, [C.POINTER(_i), C.POINTER(_i)]),
     "mgb_peer_allreduce_sum": (_i, [_vp, _sz, _i, _vp]),
     "mgb_conv_wgrad_dp": (_i, [_cdp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mgb_probe_mma_peak": (_i, [_i, _i, C.POINTER(C.c_double), _vp]),

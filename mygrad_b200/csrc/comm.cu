@@ -74,6 +74,15 @@ int load_nccl() {
 // Chunks only depend on the same chunk index on the other GPUs, so there is no grid-wide barrier;
 // slots alternate with the epoch parity: a rank can only start epoch e+2 after every peer has
 // published e+1, i.e. finished reading epoch e (kernels of one rank run in stream order).
+//
+// Forward progress and failure behaviour:
+//   * the kernel is launched COOPERATIVELY: all of its CTAs are co-resident or the launch does not start, so a
+//     CTA never waits for a peer CTA that cannot be scheduled because other work holds the SMs;
+//   * every call must be issued on ONE stream, in the same order on all ranks (epoch / slot parity are
+//     host-side counters): a call on another stream is refused;
+//   * a peer that never arrives (it failed before the collective, or was killed) no longer traps the
+//     context: after kPeerTimeoutNs the waiting CTAs give up and raise a flag in mapped host memory; the
+//     result of that call is undefined and every later call — and mgb_peer_status — reports the time-out.
 
 constexpr int kPeerMaxWorld = 16;
 constexpr int kPeerChunks = 128;            // CTAs per call == flag slots per source rank
@@ -83,6 +92,8 @@ struct PeerTable {
   char* base[kPeerMaxWorld];                // region of each rank as mapped into THIS process
 };
 
+constexpr unsigned long long kPeerTimeoutNs = 30ull * 1000 * 1000 * 1000;
+
 struct PeerState {
   bool ready = false;
   int rank = 0, world = 1;
@@ -90,6 +101,10 @@ struct PeerState {
   char* local = nullptr;
   PeerTable table{};
   uint32_t epoch = 0;
+  unsigned int* err_host = nullptr;       // mapped, pinned: [0] = epoch of the first timed-out call (0 = none), [1] = rank waited for
+  unsigned int* err_dev = nullptr;
+  bool stream_known = false;
+  cudaStream_t stream = nullptr;
 };
 PeerState g_peer;
 
@@ -115,7 +130,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) peer_reduce_allreduce_kernel(const T* partial, int splits,
                                                                     long long n, T* out,
                                                                     PeerTable tab, int rank, int world,
-                                                                    size_t slot_off, uint32_t epoch) {
+                                                                    size_t slot_off, uint32_t epoch,
+                                                                    unsigned int* err) {
   constexpr int V = 16 / (int)sizeof(T);                  // elements per 16-byte pack
   const int c = blockIdx.x;
   // chunks are whole packs, so that every remote access is one aligned 16-byte transaction
@@ -136,9 +152,18 @@ __global__ void __launch_bounds__(256) peer_reduce_allreduce_kernel(const T* par
     uint32_t* flag = reinterpret_cast<uint32_t*>(tab.base[threadIdx.x]) + rank * kPeerChunks + c;
     st_release_sys(flag, epoch);
     const uint32_t* seen = reinterpret_cast<const uint32_t*>(tab.base[rank]) + threadIdx.x * kPeerChunks + c;
-    unsigned long long spin = 0;
+    unsigned long long t0 = 0, now = 0;
+    unsigned int spin = 0;
     while ((int32_t)(ld_acquire_sys(seen) - epoch) < 0) {     // epochs only grow
-      if (++spin > (1ull << 31)) __trap();          // a peer that never arrives must not hang the GPU
+      if ((++spin & 1023u) == 0) {                  // a peer that never arrives must not hang the GPU
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > kPeerTimeoutNs) {
+          if (atomicCAS(err, 0u, epoch) == 0u) err[1] = (unsigned int)threadIdx.x;
+          __threadfence_system();
+          break;
+        }
+      }
     }
   }
   __syncthreads();
@@ -176,20 +201,34 @@ int peer_reduce_allreduce(int dtype, const void* partial, int splits, long long 
   const size_t esz = dtype == MGB_F32 ? 4 : 8;
   if ((size_t)n * esz > g_peer.slot_bytes)
     return fail("peer all-reduce: %lld elements exceed the %zu-byte slot", n, g_peer.slot_bytes);
+  if (dtype != MGB_F32 && dtype != MGB_F64) return fail("peer all-reduce: bad dtype %d", dtype);
+  if (g_peer.err_host && g_peer.err_host[0] != 0)
+    return fail("peer all-reduce: call %u timed out after %llu s waiting for rank %u — the ranks are out of step "
+                "(a rank failed before its collective, or the calls were not issued in the same order everywhere)",
+                g_peer.err_host[0], kPeerTimeoutNs / 1000000000ull, g_peer.err_host[1]);
+  if (g_peer.stream_known && st != g_peer.stream)
+    return fail("peer all-reduce: every call must be issued on one stream (epoch and slot parity assume stream "
+                "order); first call used %p, this one %p", (void*)g_peer.stream, (void*)st);
+  g_peer.stream_known = true;
+  g_peer.stream = st;
   if (n == 0) return 0;
   const uint32_t epoch = ++g_peer.epoch;
   const size_t slot_off = (epoch & 1u) ? g_peer.slot_bytes : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kPeerChunks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: cross-rank waits cannot starve
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
   if (dtype == MGB_F32)
-    peer_reduce_allreduce_kernel<float><<<kPeerChunks, 256, 0, st>>>((const float*)partial, splits, n, (float*)out,
-                                                                    g_peer.table, g_peer.rank, g_peer.world,
-                                                                    slot_off, epoch);
-  else if (dtype == MGB_F64)
-    peer_reduce_allreduce_kernel<double><<<kPeerChunks, 256, 0, st>>>((const double*)partial, splits, n,
-                                                                     (double*)out, g_peer.table, g_peer.rank,
-                                                                     g_peer.world, slot_off, epoch);
+    MGB_CUDA(cudaLaunchKernelEx(&cfg, peer_reduce_allreduce_kernel<float>, (const float*)partial, splits, n,
+                                (float*)out, g_peer.table, g_peer.rank, g_peer.world, slot_off, epoch,
+                                g_peer.err_dev));
   else
-    return fail("peer all-reduce: bad dtype %d", dtype);
-  MGB_LAUNCH_CHECK();
+    MGB_CUDA(cudaLaunchKernelEx(&cfg, peer_reduce_allreduce_kernel<double>, (const double*)partial, splits, n,
+                                (double*)out, g_peer.table, g_peer.rank, g_peer.world, slot_off, epoch,
+                                g_peer.err_dev));
+  count_launch();
   return 0;
 }
 
@@ -216,6 +255,18 @@ extern "C" int mgb_peer_create(int rank, int world_size, size_t slot_bytes, void
     return fail("cudaIpcGetMemHandle -> %s", cudaGetErrorString(e));
   }
   memcpy(ipc_handle64, &h, sizeof(h));
+  void* eh = nullptr;
+  if (cudaHostAlloc(&eh, 64, cudaHostAllocMapped) != cudaSuccess) {
+    cudaFree(ptr);
+    return fail("mgb_peer_create: cudaHostAlloc for the time-out flag failed");
+  }
+  memset(eh, 0, 64);
+  void* ed = nullptr;
+  if (cudaHostGetDevicePointer(&ed, eh, 0) != cudaSuccess) {
+    cudaFreeHost(eh); cudaFree(ptr);
+    return fail("mgb_peer_create: cudaHostGetDevicePointer failed");
+  }
+  g_peer.err_host = (unsigned int*)eh; g_peer.err_dev = (unsigned int*)ed;
   g_peer.local = (char*)ptr;
   g_peer.rank = rank; g_peer.world = world_size; g_peer.slot_bytes = slot_bytes; g_peer.epoch = 0;
   return 0;
@@ -243,7 +294,14 @@ extern "C" int mgb_peer_destroy(void) {
     for (int r = 0; r < g_peer.world; ++r)
       if (r != g_peer.rank && g_peer.table.base[r]) cudaIpcCloseMemHandle(g_peer.table.base[r]);
   cudaFree(g_peer.local);
+  if (g_peer.err_host) cudaFreeHost(g_peer.err_host);
   g_peer = PeerState{};
+  return 0;
+}
+
+extern "C" int mgb_peer_status(int* timed_out_call, int* waited_for_rank) {
+  if (timed_out_call) *timed_out_call = g_peer.err_host ? (int)g_peer.err_host[0] : 0;
+  if (waited_for_rank) *waited_for_rank = g_peer.err_host ? (int)g_peer.err_host[1] : 0;
   return 0;
 }
 

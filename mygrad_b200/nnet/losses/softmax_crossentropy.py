@@ -26,18 +26,30 @@ class SoftmaxCrossEntropy(Operation):
         # same input checks as nnet/losses/_utils.py::check_loss_inputs
         if scores.ndim != 2:
             raise ValueError(f"`x` must be a 2-dimensional array, got shape {scores.shape}")
+        # checks in the order of check_loss_inputs (nnet/losses/_utils.py:6-48): integer dtype (TypeError), then
+        # shape (ValueError).  Device-resident labels can only be float-typed here (an extension); they must
+        # hold whole numbers.
         if isinstance(y_true, DeviceArray):
             labels_host = y_true.get()
+            if not np.all(labels_host == np.round(labels_host)):
+                raise TypeError("`y_true` must hold integer class indices")
+            labels_host = labels_host.astype(np.int64)
         else:
             labels_host = np.asarray(y_true)
+            if not np.issubdtype(labels_host.dtype, np.integer):
+                raise TypeError(f"`y_true` must be an integer-type array-like object, got {labels_host.dtype}")
         if labels_host.ndim != 1 or labels_host.shape[0] != scores.shape[0]:
             raise ValueError(
-                f"`y_true` must be a 1-dimensional array of length {scores.shape[0]}, got shape {labels_host.shape}"
+                "`y_true` must be a shape-(N,) array: \n"
+                f"\tExpected shape-{(scores.shape[0],)}\n\tGot shape-{labels_host.shape}"
             )
-        if not (np.issubdtype(labels_host.dtype, np.integer) or np.all(labels_host == np.round(labels_host))):
-            raise TypeError("`y_true` must hold integer class indices")
-        if labels_host.size and (labels_host.min() < 0 or labels_host.max() >= scores.shape[1]):
-            raise ValueError("class indices in `y_true` must lie in [0, C)")
+        # the reference gathers x[range(N), y_true] (softmax_crossentropy.py:41): negative indices count from
+        # the end, anything outside [-C, C) is an IndexError
+        ncls = scores.shape[1]
+        if labels_host.size and (labels_host.min() < -ncls or labels_host.max() >= ncls):
+            bad = labels_host[(labels_host < -ncls) | (labels_host >= ncls)][0]
+            raise IndexError(f"index {bad} is out of bounds for axis 1 with size {ncls}")
+        labels_host = np.where(labels_host < 0, labels_host + ncls, labels_host)
         self.variables = (x,)
         labels = asdevice(np.ascontiguousarray(labels_host, dtype=scores.dtype))
         loss = DeviceArray((), scores.dtype)

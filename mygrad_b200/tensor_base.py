@@ -176,10 +176,18 @@ class Tensor:
         if not _track.TRACK_GRAPH:
             return cls(op_out, constant=constant, copy=False, _creator=None)
 
-        # non-view ops null the grads of their inputs (tensor_base.py:1163-1172)
-        for v in input_vars:
-            if isinstance(v, Tensor):
-                v._grad = None
+        # non-view ops null the grads of their inputs; an op whose output is a view of one of its inputs
+        # (Reshape) leaves them alone (tensor_base.py:1134-1172)
+        is_view = False
+        if f.can_return_view and op_out.base is not None:
+            for v in tensor_vars:
+                if op_out.base is v.data or op_out.base is v.data.base or op_out is v.data:
+                    is_view = True
+                    break
+        if not is_view:
+            for v in input_vars:
+                if isinstance(v, Tensor):
+                    v._grad = None
 
         if constant is None:
             constant = None if any(not v.constant for v in tensor_vars) else True

@@ -104,8 +104,16 @@ def test_softmax_crossentropy(dt):
         assert_close(x.grad.get(), back / n, dt)
     with pytest.raises(ValueError):
         softmax_crossentropy(Tensor(np.ones((3, 4), dt)), [0, 1])
-    with pytest.raises(ValueError):
+    # label conventions of the reference: fancy indexing x[range(N), y] (softmax_crossentropy.py:41) accepts
+    # negative indices and raises IndexError out of range; check_loss_inputs raises TypeError for float labels
+    with pytest.raises(IndexError):
         softmax_crossentropy(Tensor(np.ones((3, 4), dt)), [0, 1, 4])
+    with pytest.raises(TypeError):
+        softmax_crossentropy(Tensor(np.ones((3, 4), dt)), [0.0, 1.0, 2.0])
+    xs = np.random.default_rng(3).standard_normal((3, 4)).astype(dt)
+    a = softmax_crossentropy(Tensor(xs), [-1, 0, -4])
+    b = softmax_crossentropy(Tensor(xs), [3, 0, 0])
+    assert a.item() == b.item()
 
 
 def test_reshape_is_a_view_and_backprops():
@@ -115,3 +123,17 @@ def test_reshape_is_a_view_and_backprops():
     assert r.shape == (6, 4) and r.data.ptr == x.data.ptr
     r.backward(np.arange(24.0).reshape(6, 4))
     np.testing.assert_array_equal(x.grad.get(), xh)
+
+
+def test_view_ops_do_not_null_the_grads_of_their_inputs():
+    """tensor_base.py:1134-1172: only NON-view ops clear the grads of their inputs"""
+    from mygrad_b200.nnet.layers import conv_nd
+
+    rng = np.random.default_rng(1)
+    x = Tensor(rng.standard_normal((2, 3, 4)))
+    (x + 1.0).backward()
+    assert x.grad is not None
+    _ = x.reshape(6, 4)                 # a view: x.grad survives
+    assert x.grad is not None
+    _ = x + 2.0                         # not a view: nulled
+    assert x.grad is None
