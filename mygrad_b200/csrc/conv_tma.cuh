@@ -297,6 +297,24 @@ __device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* ma
       "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same box written to the same shared-memory offset of every CTA in `mask`; each destination CTA's
+// barrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_5d_mc(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                               int c1, int c2, int c3, int c4, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;\n" ::"r"(dst),
+      "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(mask)
+      : "memory");
+}
+// single-CTA MMAs, but "done" is signalled to the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+          tc::smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                            uint32_t accumulate) {
   asm volatile(
@@ -518,6 +536,11 @@ struct WgradTmaParams {
   int blocked;
   int X0, G0;                              // outermost spatial extents of x and dy (for the merged axis)
   unsigned long long* prof;                // diagnostics (MGB_WGRAD_PROF): per-CTA cycle counters of the MMA thread
+  // mc > 1: the `mc` CTAs along blockIdx.y (the N tiles of one F tile and K split) form a thread-block
+  // cluster and share the dy operand: CTA 0 fetches the hi plane, CTA 1 the lo plane, each ONCE, multicast
+  // into the shared memory of all of them (the kernel is bound by L2 -> SM bytes; dy was fetched mc times).
+  // "Stage free" commits are multicast too: a stage is refilled only when every CTA has consumed it.
+  int mc;
 };
 
 inline size_t wgrad_smem_bytes(int nbpc, int stages, int pix) {
@@ -548,11 +571,14 @@ wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant
   const int kb1 = min(p.boxes_total, kb0 + p.boxes_per_split);
   const int S = max(0, kb1 - kb0);
 
+  const int mc = p.mc;
+  const uint32_t crank = mc > 1 ? cluster_ctarank() : 0u;
+  const uint16_t mc_mask = (uint16_t)((1u << mc) - 1u);
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_dy_hi); prefetch_tmap(&map_dy_lo); prefetch_tmap(&map_x_hi); prefetch_tmap(&map_x_lo);
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(full_bar + s, 1);
-      tc::mbar_init(empty_bar + s, 1);
+      tc::mbar_init(empty_bar + s, (uint32_t)mc);      // one (multicast) commit per CTA of the cluster
     }
     tc::mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -560,6 +586,7 @@ wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant
   if (warp == 1) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc::tc_fence_before();
   __syncthreads();
+  if (mc > 1) cluster_sync_all();             // every CTA's barriers exist before a peer's TMA or commit signals them
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem_base = tc::smem_u32(smem);
@@ -584,8 +611,13 @@ wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant
         if (p.blocked) {
           // coordinates (ch-in-block, x2, x1, u = n*X0 + x0, block)
           const int uy = n0 * p.G0 + g0, ux = n0 * p.X0 + x0;
-          tma_load_5d(a_hi, &map_dy_hi, full_bar + stage, 0, g2, g1, uy, m0 / 32);
-          tma_load_5d(a_hi + a_plane, &map_dy_lo, full_bar + stage, 0, g2, g1, uy, m0 / 32);
+          if (mc > 1) {
+            if (crank == 0u) tma_load_5d_mc(a_hi, &map_dy_hi, full_bar + stage, 0, g2, g1, uy, m0 / 32, mc_mask);
+            if (crank == 1u) tma_load_5d_mc(a_hi + a_plane, &map_dy_lo, full_bar + stage, 0, g2, g1, uy, m0 / 32, mc_mask);
+          } else {
+            tma_load_5d(a_hi, &map_dy_hi, full_bar + stage, 0, g2, g1, uy, m0 / 32);
+            tma_load_5d(a_hi + a_plane, &map_dy_lo, full_bar + stage, 0, g2, g1, uy, m0 / 32);
+          }
           for (int b = 0; b < nvalid; b += p.cblocks) {
             const int tap = (blk0 + b) / p.cblocks;
             const int4 tv = __ldg(reinterpret_cast<const int4*>(p.taps) + tap);
@@ -638,7 +670,8 @@ wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant
           tc::umma_tf32(tmem_base, dah, dbl, idesc, 1u);
           tc::umma_tf32(tmem_base, dah, dbh, idesc, 1u);
         }
-        tc::umma_commit(empty_bar + stage);
+        if (mc > 1) umma_commit_mc(empty_bar + stage, mc_mask);
+        else tc::umma_commit(empty_bar + stage);
       }
       if (S > 0) tc::umma_commit(accum_bar);
       if (p.prof) {
@@ -680,6 +713,7 @@ wgrad_tma_kernel(const __grid_constant__ WgradTmaParams p, const __grid_constant
 
   tc::tc_fence_before();
   __syncthreads();
+  if (mc > 1) cluster_sync_all();             // no CTA leaves while a peer may still write into it or signal it
   if (warp == 1) tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
