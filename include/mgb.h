@@ -128,6 +128,12 @@ int mgb_conv_pool_fwd(const mgb_conv_desc* d, const mgb_pool_desc* pd, const voi
 /* dy_planes: mgb_conv_planes_bytes(d, 1) bytes, as made by mgb_conv_make_planes(d, 1, dy, ...) */
 int mgb_pool_bwd_planes(const mgb_conv_desc* d, const mgb_pool_desc* pd, const void* dp,
                         const void* argmax, void* dy_planes, void* stream);
+/* The unfused pair's transparent half of the fusion: MaxPoolND.backward_var (pooling.py:100-149) of a tensor
+ * that a conv_nd produced writes dy (y.grad, as always) AND the channels-last dy planes the convolution's
+ * backward reads, in one pass over y and dp — replaces mgb_pool_bwd + mgb_conv_make_planes(d, 1, ...); same
+ * geometry as above.  dy is bit-identical to mgb_pool_bwd's, the planes to mgb_conv_make_planes'. */
+int mgb_pool_bwd_dy_planes(const mgb_conv_desc* d, const mgb_pool_desc* pd, const void* dp, const void* y,
+                           void* dy, void* dy_planes, void* stream);
 
 /* ---- Tensor.backward reductions / element-wise --------------------------- */
 

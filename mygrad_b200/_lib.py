@@ -68,6 +68,7 @@ EXPORTS = {
     "mgb_conv_pool_supported": (_i, [_cdp, _pdp, C.POINTER(_i)]),
     "mgb_conv_pool_fwd": (_i, [_cdp, _pdp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mgb_pool_bwd_planes": (_i, [_cdp, _pdp, _vp, _vp, _vp, _vp]),
+    "mgb_pool_bwd_dy_planes": (_i, [_cdp, _pdp, _vp, _vp, _vp, _vp, _vp]),
     "mgb_pool_fwd": (_i, [_pdp, _vp, _vp, _vp]),
     "mgb_pool_bwd": (_i, [_pdp, _vp, _vp, _vp, _vp]),
     "mgb_reduce_broadcast": (_i, [_i, _i, _i64p, _i, _i64p, _vp, _vp, _i, _vp]),

@@ -1199,13 +1199,16 @@ bool conv_pool_applies(const Plan& p, const mgb_pool_desc* pd) {
 // kernels read (never as an NCHW tensor): dy[n][h][w][f] = dp[n][f][h/2][w/2] where the window's first
 // maximum sits, else 0 (pooling.py:109-149 for a tiling pool).  A CTA turns 32 channels x 64 pooled pixels
 // of dp / argmax (read along the pixels) into 256 output pixels x 128 B per plane (written along the channels).
+template <bool FROM_Y>
 __global__ void __launch_bounds__(256) pool_bwd_planes_kernel(const float* __restrict__ dp,
                                                               const unsigned char* __restrict__ am,
+                                                              const float* __restrict__ y, float* __restrict__ dy,
                                                               float* __restrict__ hi, float* __restrict__ lo,
                                                               int F, int PH, int PW, int cpad) {
   __shared__ float val[32][65];
   __shared__ unsigned char pos[32][68];
   const int PP = PH * PW;
+  const int W = 2 * PW;
   const int q0 = blockIdx.x * 64, c0 = blockIdx.y * 32, n = blockIdx.z;
   {
     const int ch = threadIdx.x >> 3, g = threadIdx.x & 7;       // 8 threads x 8 pooled pixels per channel
@@ -1218,14 +1221,30 @@ __global__ void __launch_bounds__(256) pool_bwd_planes_kernel(const float* __res
       if (c < F && q < PP) {
         const long long o = ((long long)n * F + c) * PP + q;
         v = __ldg(dp + o);
-        a = __ldg(am + o);
+        if (FROM_Y) {
+          // the unfused layer: recompute the window's first maximum from y (pooling.py:111) and write dy
+          // (the public y.grad) in the same pass; 8-byte accesses, two rows per window
+          const int ph = q / PW, pw = q - ph * PW;
+          const long long yo = ((long long)n * F + c) * (4LL * PP) + (long long)(2 * ph) * W + 2 * pw;
+          const float2 r0 = __ldg(reinterpret_cast<const float2*>(y + yo));
+          const float2 r1 = __ldg(reinterpret_cast<const float2*>(y + yo + W));
+          float b = r0.x;
+          int k = 0;
+          if (r0.y > b || (r0.y != r0.y && b == b)) { b = r0.y; k = 1; }
+          if (r1.x > b || (r1.x != r1.x && b == b)) { b = r1.x; k = 2; }
+          if (r1.y > b || (r1.y != r1.y && b == b)) { b = r1.y; k = 3; }
+          a = (unsigned char)k;
+          *reinterpret_cast<float2*>(dy + yo) = make_float2(k == 0 ? v : 0.f, k == 1 ? v : 0.f);
+          *reinterpret_cast<float2*>(dy + yo + W) = make_float2(k == 2 ? v : 0.f, k == 3 ? v : 0.f);
+        } else {
+          a = __ldg(am + o);
+        }
       }
       val[ch][g + 8 * i] = v;
       pos[ch][g + 8 * i] = a;
     }
   }
   __syncthreads();
-  const int W = 2 * PW;
   const int cq = threadIdx.x & 7;                               // 8 lanes = the 32 channels of one output pixel
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
@@ -1511,8 +1530,30 @@ extern "C" int mgb_pool_bwd_planes(const mgb_conv_desc* d, const mgb_pool_desc* 
   TcPlanes P = tc_planes(0, p.N, p.F, p.Gp);
   const int PH = p.G[1] / 2, PW = p.G[2] / 2;
   dim3 grid((unsigned)((PH * PW + 63) / 64), (unsigned)(P.cpad / 32), (unsigned)p.N);
-  pool_bwd_planes_kernel<<<grid, 256, 0, as_stream(stream)>>>(
-      (const float*)dp, (const unsigned char*)argmax, (float*)((char*)dy_planes + P.hi_off),
+  pool_bwd_planes_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(
+      (const float*)dp, (const unsigned char*)argmax, nullptr, nullptr, (float*)((char*)dy_planes + P.hi_off),
+      (float*)((char*)dy_planes + P.lo_off), (int)p.F, PH, PW, P.cpad);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
+// max_pool backward of a conv_nd output, for the UNFUSED pair: dy (the public y.grad) and the channels-last
+// planes of dy that the convolution's dX / dW read, in one pass over y and dp (instead of mgb_pool_bwd followed by
+// mgb_conv_make_planes, which re-reads dy).  Same geometry as the fused pair; 8-byte alignment of y / dy rows
+// (even conv output width) is part of that geometry.
+extern "C" int mgb_pool_bwd_dy_planes(const mgb_conv_desc* d, const mgb_pool_desc* pd, const void* dp, const void* y,
+                                      void* dy, void* dy_planes, void* stream) {
+  Plan p;
+  if (make_plan(d, &p)) return 1;
+  if (!conv_pool_applies(p, pd)) return fail("mgb_pool_bwd_dy_planes: geometry not supported by the fused kernels");
+  if (!dp || !y || !dy || !dy_planes) return fail("mgb_pool_bwd_dy_planes: null buffer");
+  if (((uintptr_t)y | (uintptr_t)dy) & 7) return fail("mgb_pool_bwd_dy_planes: y and dy must be 8-byte aligned");
+  if (p.N > 65535) return fail("mgb_pool_bwd_dy_planes: batch %lld > 65535 unsupported", p.N);
+  TcPlanes P = tc_planes(0, p.N, p.F, p.Gp);
+  const int PH = p.G[1] / 2, PW = p.G[2] / 2;
+  dim3 grid((unsigned)((PH * PW + 63) / 64), (unsigned)(P.cpad / 32), (unsigned)p.N);
+  pool_bwd_planes_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(
+      (const float*)dp, nullptr, (const float*)y, (float*)dy, (float*)((char*)dy_planes + P.hi_off),
       (float*)((char*)dy_planes + P.lo_off), (int)p.F, PH, PW, P.cpad);
   MGB_LAUNCH_CHECK();
   return 0;

@@ -150,7 +150,11 @@ class ConvND(Operation):
     def backward_var(self, grad: DeviceArray, index: int, **kwargs) -> DeviceArray:
         g = grad.astype(self._dtype, copy=False)
         if index == 0:  # dX, shape of x, dtype of x (conv.py:118)
-            self._dy_planes = (g.ptr, self._make_planes(1, g))
+            # planes of exactly this gradient may already exist: MaxPoolND.backward_var writes them together
+            # with dy when it feeds a convolution (pooling.py: the transparent half of the conv -> pool fusion)
+            cached = self._dy_planes
+            if cached is None or cached[0] != g.ptr:
+                self._dy_planes = (g.ptr, self._make_planes(1, g))
             return self._dgrad(g, self._dy_planes[1])
         # dW: dy planes made by the dX pass of the same backward call are valid for this grad only
         cached = self._dy_planes

@@ -14,6 +14,7 @@ composition ``sliding_window_view(x, pool, stride).mean(axis=pool_axes)``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from numbers import Integral
 from typing import Optional, Tuple, Union
 
@@ -104,9 +105,39 @@ class MaxPoolND(Operation):
             return grad.copy()
         g = grad.astype(xd.dtype, copy=False)
         dx = DeviceArray(xd.shape, xd.dtype)
+        if self._feeds_conv_planes(g, xd, dx):
+            return dx
         check(lib.mgb_pool_bwd(C.byref(self._desc), C.c_void_p(g.ptr), C.c_void_p(xd.ptr),
                                C.c_void_p(dx.ptr), C.c_void_p(current_stream())))
         return dx
+
+
+    def _feeds_conv_planes(self, g: DeviceArray, yd: DeviceArray, dy: DeviceArray) -> bool:
+        """The transparent half of the conv -> pool fusion for the drop-in pair
+        ``max_pool(conv_nd(...))``: when the pooled tensor was produced by a float32 tensor-core convolution and
+        nothing else consumes it, one kernel writes dy — the public ``y.grad``, bit-identical to ``mgb_pool_bwd``'s —
+        AND the channels-last hi/lo planes of dy that the convolution's dX / dW read, instead of a second pass
+        over dy (``mgb_conv_make_planes``).  The planes are handed to the ConvND op keyed by dy's pointer."""
+        from .conv import ConvND
+
+        y = self.variables[0]
+        conv = y.creator
+        if self._mode != 0 or not isinstance(conv, ConvND) or len(y._ops) != 1 or yd.dtype != np.float32:
+            return False
+        if os.environ.get("MGB_POOL_FEEDS_CONV", "1") == "0":      # A/B switch for tests and measurements
+            return False
+        yes = C.c_int(0)
+        check(lib.mgb_conv_pool_supported(C.byref(conv._desc), C.byref(self._desc), C.byref(yes)))
+        if not yes.value:
+            return False
+        n = C.c_size_t(0)
+        check(lib.mgb_conv_planes_bytes(C.byref(conv._desc), 1, C.byref(n)))
+        planes = DeviceArray(((n.value + 7) // 8,), np.float64)
+        check(lib.mgb_pool_bwd_dy_planes(C.byref(conv._desc), C.byref(self._desc), C.c_void_p(g.ptr),
+                                         C.c_void_p(yd.ptr), C.c_void_p(dy.ptr), C.c_void_p(planes.ptr),
+                                         C.c_void_p(current_stream())))
+        conv._dy_planes = (dy.ptr, planes)
+        return True
 
 
 class MeanPoolND(MaxPoolND):

@@ -12,6 +12,7 @@ run 29621 bench.py --gpus $N --steps $K --warmup 3 --workload C2 > gpurun_out/sc
 run 29622 bench.py --gpus $N --steps $K --warmup 3 --workload C2 --scaling strong --no-e2e > gpurun_out/scale_C2_strong_n$N.json 2> gpurun_out/scale_C2_strong_n$N.err; echo "C2 strong rc=$?"
 run 29623 bench.py --gpus $N --steps $K --warmup 3 --workload C4 --scaling strong --no-e2e > gpurun_out/scale_C4_strong_n$N.json 2> gpurun_out/scale_C4_strong_n$N.err; echo "C4 strong rc=$?"
 run 29624 bench.py --gpus $N --steps $K --warmup 3 --workload C5 > gpurun_out/scale_C5_weak_n$N.json 2> gpurun_out/scale_C5_weak_n$N.err; echo "C5 weak rc=$?"
+run 29625 scripts/allreduce_bench.py > gpurun_out/allreduce_n$N.json 2> gpurun_out/allreduce_n$N.err; echo "allreduce bench rc=$?"; tail -1 gpurun_out/allreduce_n$N.json | cut -c1-600
 for f in C2_weak C2_strong C4_strong C5_weak; do
   python - "$f" "$N" <<'PY'
 import json, sys

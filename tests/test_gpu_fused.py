@@ -207,3 +207,60 @@ def test_c_abi_fused_entry_points_reject_unsupported_geometry():
     assert lib.mgb_conv_pool_supported(C.byref(cd), C.byref(pd), C.byref(yes)) == 0 and yes.value == 0
     assert lib.mgb_conv_pool_fwd(C.byref(cd), C.byref(pd), None, None, None, None, None, None, 0, None) != 0
     assert b"not supported" in lib.mgb_last_error()
+
+
+def test_unfused_pair_pool_backward_feeds_the_conv_planes(monkeypatch):
+    """max_pool(conv_nd(...)).backward(): when the pooled tensor comes from a tensor-core convolution and has no
+    other consumer, MaxPoolND.backward_var writes dy AND the convolution's dy planes in one kernel.  y.grad, x.grad
+    and w.grad must be bit-identical to the two-kernel path (mgb_pool_bwd + mgb_conv_make_planes)."""
+    rng = np.random.default_rng(17)
+    x = rng.standard_normal((3, 32, 12, 20)).astype(np.float32)
+    w = rng.standard_normal((48, 32, 3, 3)).astype(np.float32)
+    g = rng.standard_normal((3, 48, 6, 10)).astype(np.float32)
+
+    def run():
+        xt, wt = Tensor(x), Tensor(w)
+        y = conv_nd(xt, wt, stride=1, padding=1)
+        o = max_pool(y, (2, 2), 2)
+        conv_op = y.creator
+        o.backward(g)
+        return y.grad.get(), xt.grad.get(), wt.grad.get(), conv_op
+
+    monkeypatch.setenv("MGB_POOL_FEEDS_CONV", "0")
+    want = run()
+    monkeypatch.setenv("MGB_POOL_FEEDS_CONV", "1")
+    n0 = C_launches()
+    got = run()
+    one_pass = C_launches() - n0
+    monkeypatch.setenv("MGB_POOL_FEEDS_CONV", "0")
+    n0 = C_launches()
+    run()
+    two_pass = C_launches() - n0
+    assert one_pass == two_pass - 1, (one_pass, two_pass)        # plane prep of dy folded into the pool backward
+    for nm, a, b in zip(("dy", "dx", "dw"), got, want):
+        np.testing.assert_array_equal(a, b, err_msg=nm)
+    yh = oc.conv_fwd(x, w, 1, 1, 1)
+    # x constant: only dW runs and must still find the planes
+    monkeypatch.setenv("MGB_POOL_FEEDS_CONV", "1")
+    xt, wt = Tensor(x, constant=True), Tensor(w)
+    max_pool(conv_nd(xt, wt, stride=1, padding=1), (2, 2), 2).backward(g)
+    np.testing.assert_array_equal(wt.grad.get(), want[2])
+    # a second consumer of y: grads accumulate into y.grad, so the planes of the pool's contribution alone
+    # would be stale — the one-pass path must stay out of the way
+    xt, wt = Tensor(x), Tensor(w)
+    y = conv_nd(xt, wt, stride=1, padding=1)
+    o1, o2 = max_pool(y, (2, 2), 2), max_pool(y, (2, 2), 2)
+    (o1 + o2).backward(g)
+    np.testing.assert_array_equal(y.grad.get(), 2 * want[0])
+    assert_close(xt.grad.get(), 2 * want[1], np.float32)
+    assert_close(wt.grad.get(), 2 * want[2], np.float32)
+
+
+def C_launches() -> int:
+    import ctypes as C
+
+    from mygrad_b200._lib import lib
+
+    n = C.c_uint64(0)
+    lib.mgb_launch_count(C.byref(n))
+    return int(n.value)
