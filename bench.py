@@ -456,6 +456,15 @@ class Harness:
             yes = C.c_int(0)
             check(lib.mgb_conv_pool_supported(C.byref(cd), C.byref(pd), C.byref(yes)))
             if yes.value and dy_planes is not None:
+                # what the drop-in pair runs instead of pool_bwd + plane_prep_dy: dy and its planes in one pass
+                dyp1, gy3 = mg.empty((dy_planes.size,), np.float64), mg.empty(y.shape, dt)
+                phases["pool_bwd_dy_planes"] = {"ms": timed(lambda: check(lib.mgb_pool_bwd_dy_planes(
+                    C.byref(cd), C.byref(pd), P(gp), P(y), P(gy3), P(dyp1), stream))),
+                    "bytes": 4 * geo["y_bytes"] + geo["p_bytes"],
+                    "note": "replaces pool_bwd + plane_prep_dy in the step (y + dp in; dy + hi/lo planes out)"}
+                phases["pool_bwd"]["two_pass_only"] = True
+                phases["plane_prep_dy"]["two_pass_only"] = True
+                del dyp1, gy3
                 am = mg.empty(((pooled.size + 3) // 4,), np.float32)
                 phases["fused_conv_pool_fwd"] = {"ms": timed(lambda: check(lib.mgb_conv_pool_fwd(
                     C.byref(cd), C.byref(pd), P(x_dev), P(w_dev), P(pooled), P(am), PN(x_planes), P(wss[0][0]),

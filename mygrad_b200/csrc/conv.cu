@@ -1211,37 +1211,42 @@ __global__ void __launch_bounds__(256) pool_bwd_planes_kernel(const float* __res
   const int W = 2 * PW;
   const int q0 = blockIdx.x * 64, c0 = blockIdx.y * 32, n = blockIdx.z;
   {
-    const int ch = threadIdx.x >> 3, g = threadIdx.x & 7;       // 8 threads x 8 pooled pixels per channel
-    const int c = c0 + ch;
+    // a warp walks 4 channels; its 32 lanes cover 32 consecutive windows of one channel, so every access is a
+    // contiguous run (128 B of dp, 256 B per row of y / dy) instead of eight 32-byte pieces
+    const int lane = threadIdx.x & 31, w4 = (threadIdx.x >> 5) * 4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int q = q0 + g + 8 * i;                             // consecutive threads -> consecutive pixels
-      float v = 0.f;
-      unsigned char a = 255;
-      if (c < F && q < PP) {
-        const long long o = ((long long)n * F + c) * PP + q;
-        v = __ldg(dp + o);
-        if (FROM_Y) {
-          // the unfused layer: recompute the window's first maximum from y (pooling.py:111) and write dy
-          // (the public y.grad) in the same pass; 8-byte accesses, two rows per window
-          const int ph = q / PW, pw = q - ph * PW;
-          const long long yo = ((long long)n * F + c) * (4LL * PP) + (long long)(2 * ph) * W + 2 * pw;
-          const float2 r0 = __ldg(reinterpret_cast<const float2*>(y + yo));
-          const float2 r1 = __ldg(reinterpret_cast<const float2*>(y + yo + W));
-          float b = r0.x;
-          int k = 0;
-          if (r0.y > b || (r0.y != r0.y && b == b)) { b = r0.y; k = 1; }
-          if (r1.x > b || (r1.x != r1.x && b == b)) { b = r1.x; k = 2; }
-          if (r1.y > b || (r1.y != r1.y && b == b)) { b = r1.y; k = 3; }
-          a = (unsigned char)k;
-          *reinterpret_cast<float2*>(dy + yo) = make_float2(k == 0 ? v : 0.f, k == 1 ? v : 0.f);
-          *reinterpret_cast<float2*>(dy + yo + W) = make_float2(k == 2 ? v : 0.f, k == 3 ? v : 0.f);
-        } else {
-          a = __ldg(am + o);
+    for (int k = 0; k < 4; ++k) {
+      const int ch = w4 + k, c = c0 + ch;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int ql = lane + 32 * i, q = q0 + ql;
+        float v = 0.f;
+        unsigned char a = 255;
+        if (c < F && q < PP) {
+          const long long o = ((long long)n * F + c) * PP + q;
+          v = __ldg(dp + o);
+          if (FROM_Y) {
+            // the unfused layer: recompute the window's first maximum from y (pooling.py:111) and write dy
+            // (the public y.grad) in the same pass; 8-byte accesses, two rows per window
+            const int ph = q / PW, pw = q - ph * PW;
+            const long long yo = ((long long)n * F + c) * (4LL * PP) + (long long)(2 * ph) * W + 2 * pw;
+            const float2 r0 = __ldg(reinterpret_cast<const float2*>(y + yo));
+            const float2 r1 = __ldg(reinterpret_cast<const float2*>(y + yo + W));
+            float b = r0.x;
+            int kk = 0;
+            if (r0.y > b || (r0.y != r0.y && b == b)) { b = r0.y; kk = 1; }
+            if (r1.x > b || (r1.x != r1.x && b == b)) { b = r1.x; kk = 2; }
+            if (r1.y > b || (r1.y != r1.y && b == b)) { b = r1.y; kk = 3; }
+            a = (unsigned char)kk;
+            *reinterpret_cast<float2*>(dy + yo) = make_float2(kk == 0 ? v : 0.f, kk == 1 ? v : 0.f);
+            *reinterpret_cast<float2*>(dy + yo + W) = make_float2(kk == 2 ? v : 0.f, kk == 3 ? v : 0.f);
+          } else {
+            a = __ldg(am + o);
+          }
         }
+        val[ch][ql] = v;
+        pos[ch][ql] = a;
       }
-      val[ch][g + 8 * i] = v;
-      pos[ch][g + 8 * i] = a;
     }
   }
   __syncthreads();
