@@ -11,6 +11,7 @@
 #include "conv_tma.cuh"
 #include "conv_halo.cuh"
 #include "conv_halo2.cuh"
+#include "conv_wgrad2.cuh"
 
 namespace mgb {
 namespace conv {
@@ -1115,6 +1116,114 @@ int wgrad_tma_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const fl
   return 0;
 }
 
+
+// ---- wgrad with a row halo of x (conv_wgrad2.cuh): returns 0 ok, 1 error, 2 not applicable ----
+// MGB_WGRAD_ROWS: unset = when the N tile is at least 128 columns wide, "0" = never, "1" = whenever legal
+int wgrad_rows_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const float* xlo, const float* yhi,
+                      const float* ylo, float* partial, cudaStream_t st) {
+  EncodeTiledFn enc = tma_encoder();
+  const char* er = getenv("MGB_WGRAD_ROWS");
+  if (!enc || !tma_enabled() || (er && er[0] == '0')) return 2;
+  for (int i = 0; i < 3; ++i) if (p.X[i] < 1 || p.G[i] < 1) return 2;
+  const bool flat = p.X[0] == 1 && p.G[0] == 1;              // <= 2 spatial dims
+  const bool mergeable = !flat && p.Pd[0] == 0;               // 3-D with an unpadded outer axis
+  if (!(flat || mergeable) || p.S[1] != 1) return 2;
+  // c-blocks per CTA: the N tile is W1 * cbc blocks of 32 columns, at most 8
+  int cbc = 0;
+  for (int c = L.cblocks; c >= 1; --c)
+    if (L.cblocks % c == 0 && p.W[1] * c <= 8) { cbc = c; break; }
+  if (cbc == 0 || (cbc > 1 && p.D[1] != 1)) return 2;
+  const int ncols = p.W[1] * cbc * 32;
+  if (ncols < 128 && !(er && er[0] == '1')) return 2;
+  const int ext = (p.W[1] - 1) * p.D[1];
+  // pixel box b1 x b2 = 32 with b2 >= 4: fewest x bytes per stage over all boxes
+  int b1 = 0, b2 = 0;
+  long long best = -1;
+  for (int c2 = 4; c2 <= 32; c2 <<= 1) {
+    const int c1 = 32 / c2;
+    if (c2 * p.S[2] > 256 || c1 + ext > 256) continue;
+    const long long tiles = (long long)((p.G[1] + c1 - 1) / c1) * ((p.G[2] + c2 - 1) / c2);
+    const long long cost = tiles * ((long long)(c1 + ext) * c2 * cbc + 4 * 32);     // x rows + dy, in 128-byte rows per plane
+    if (best < 0 || cost < best) { best = cost; b1 = c1; b2 = c2; }
+  }
+  if (best < 0) return 2;
+  tma::WgradRowsParams wp;
+  wp.b1 = b1; wp.b2 = b2;
+  wp.tiles1 = (p.G[1] + b1 - 1) / b1; wp.tiles2 = (p.G[2] + b2 - 1) / b2;
+  wp.G0 = p.G[0]; wp.X0 = p.X[0];
+  wp.S0 = p.S[0]; wp.S2 = p.S[2]; wp.Pd1 = p.Pd[1]; wp.Pd2 = p.Pd[2];
+  wp.D0 = p.D[0]; wp.D1 = p.D[1]; wp.D2 = p.D[2];
+  wp.W0 = p.W[0]; wp.W1 = p.W[1]; wp.W2 = p.W[2];
+  wp.F = (int)p.F; wp.C = (int)p.C; wp.Wp = (int)p.Wp; wp.cblocks = L.cblocks; wp.cbc = cbc;
+  wp.rows = b1 + ext;
+  wp.tmem_cols = pow2_cols(ncols);
+  const long long boxes = (long long)p.N * p.G[0] * wp.tiles1 * wp.tiles2;
+  if (boxes > INT32_MAX || (long long)p.N * std::max(p.G[0], p.X[0]) > INT32_MAX) return 2;
+  const int ny = p.W[0] * p.W[2] * (L.cblocks / cbc);
+  int splits = (int)std::max<long long>(1, std::min<long long>(std::max(1, sm_count() / (L.mt * ny)), boxes / 8));
+  const long long per = (boxes + splits - 1) / splits;
+  splits = (int)((boxes + per - 1) / per);
+  if ((size_t)splits * p.F * p.C * p.Wp * sizeof(float) > L.end - L.partial_off) return 2;
+  wp.boxes_total = (int)boxes; wp.boxes_per_split = (int)per;
+  wp.partial = partial;
+  // dy: (32, G2, G1, N*G0, Fpad/32), box (32, b2, b1, 1, 4) -> [f-block][row][column][128 B]
+  // x : (32, X2, Cpad/32, X1, N*X0), box (32, b2 (stride S2), cbc, rows, 1) -> [row][c-block][column][128 B]
+  CUtensorMap mdy_hi, mdy_lo, mx_hi, mx_lo;
+  auto encode_dy = [&](CUtensorMap* m, const float* base) {
+    const cuuint64_t row = (cuuint64_t)L.Y.cpad * 4;
+    cuuint64_t dims[5] = {32, (cuuint64_t)p.G[2], (cuuint64_t)p.G[1], (cuuint64_t)p.N * p.G[0], (cuuint64_t)L.Y.cpad / 32};
+    cuuint64_t strides[4] = {row, row * p.G[2], row * p.G[2] * p.G[1], 128};
+    cuuint32_t box[5] = {32, (cuuint32_t)b2, (cuuint32_t)b1, 1, 4};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  auto encode_x = [&](CUtensorMap* m, const float* base) {
+    const cuuint64_t row = (cuuint64_t)L.X.cpad * 4;
+    cuuint64_t dims[5] = {32, (cuuint64_t)p.X[2], (cuuint64_t)L.X.cpad / 32, (cuuint64_t)p.X[1], (cuuint64_t)p.N * p.X[0]};
+    cuuint64_t strides[4] = {row, 128, row * p.X[2], row * p.X[2] * p.X[1]};
+    cuuint32_t box[5] = {32, (cuuint32_t)(b2 * p.S[2]), (cuuint32_t)cbc, (cuuint32_t)wp.rows, 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)p.S[2], 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  if (!encode_dy(&mdy_hi, yhi) || !encode_dy(&mdy_lo, ylo) || !encode_x(&mx_hi, xhi) || !encode_x(&mx_lo, xlo)) return 2;
+  wp.prof = nullptr;
+  static unsigned long long* wprof = nullptr;
+  const long long nctas = (long long)L.mt * ny * splits;
+  if (getenv("MGB_WGRAD_PROF") && nctas <= 4096) {
+    if (!wprof) MGB_CUDA(cudaMalloc(&wprof, 4096 * 4 * sizeof(unsigned long long)));
+    MGB_CUDA(cudaMemsetAsync(wprof, 0, 4096 * 4 * sizeof(unsigned long long), st));
+    wp.prof = wprof;
+  }
+  const size_t stage = 2 * 4 * 32 * 128 + 2 * (size_t)wp.rows * cbc * b2 * 128;
+  const int stages = (int)std::min<size_t>(4, (227 * 1024 - 1280) / stage);
+  if (stages < 2) return 2;
+  auto launch = [&](auto kern) -> int {
+    const size_t smem = tma::wgrad_rows_smem_bytes(wp.rows, cbc, b2, stages);
+    MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(L.mt, ny, splits), tma::THREADS, smem, st>>>(wp, mdy_hi, mdy_lo, mx_hi, mx_lo);
+    return 0;
+  };
+  int rc = stages == 4 ? launch(tma::wgrad_rows_kernel<4>) : stages == 3 ? launch(tma::wgrad_rows_kernel<3>)
+                                                                        : launch(tma::wgrad_rows_kernel<2>);
+  if (rc) return rc;
+  MGB_LAUNCH_CHECK();
+  L.tma_splits = splits;
+  if (wp.prof) {
+    std::vector<unsigned long long> h((size_t)nctas * 4);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), wprof, h.size() * 8, cudaMemcpyDeviceToHost);
+    double wf = 0, tot = 0, S = 0;
+    for (long long i = 0; i < nctas; ++i) { wf += (double)h[4 * i]; tot += (double)h[4 * i + 1]; S += (double)h[4 * i + 2]; }
+    fprintf(stderr, "[wgrad prof rows] %lld CTAs, box %dx%d, %d halo rows, N %d, %d stages of %zu B: per stage wait full %.0f, total %.0f clk (tensor floor %.0f)\n",
+            nctas, b1, b2, wp.rows, ncols, stages, stage, wf / S, tot / S, 4 * 3.0 * ncols / 2);
+  }
+  return 0;
+}
+
 int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, const void* dy_planes,
              const void* x_planes, void* ws, size_t ws_bytes, cudaStream_t st) {
   long long n_dw = p.F * p.C * p.Wp;
@@ -1152,9 +1261,10 @@ int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, const vo
   for (int i = 0; i < 3; ++i) { wp.G[i] = p.G[i]; wp.S[i] = p.S[i]; wp.Pd[i] = p.Pd[i]; wp.X[i] = p.X[i]; }
   wp.gp = (int)p.Gp; wp.Ktot = (int)(p.N * p.Gp); wp.k_per_split = L.kps;
   wp.nblocks_total = L.nblocks; wp.nbpc = L.nbpc; wp.tmem_cols = pow2_cols(L.nbpc * 32);
-  // TMA-staged variant first; the cp.async kernel is the fallback
+  // row-halo variant, then the per-tap TMA variant; the cp.async kernel is the fallback
   {
-    int rc = wgrad_tma_launch(p, L, xhi, xlo, yhi, ylo, taps, partial, st);
+    int rc = wgrad_rows_launch(p, L, xhi, xlo, yhi, ylo, partial, st);
+    if (rc == 2) rc = wgrad_tma_launch(p, L, xhi, xlo, yhi, ylo, taps, partial, st);
     if (rc == 1) return 1;
     if (rc == 0) {
       return finish_dw<float>(partial, dw, n_dw, L.tma_splits, st);
