@@ -12,6 +12,7 @@
 #include "conv_halo.cuh"
 #include "conv_halo2.cuh"
 #include "conv_wgrad2.cuh"
+#include "conv_f64_tma.cuh"
 
 namespace mgb {
 namespace conv {
@@ -281,6 +282,8 @@ XTableArgs x_table_args(const Plan& p) {
   return a;
 }
 
+inline int round_up(long long v, int m) { return (int)((v + m - 1) / m * m); }
+
 inline long long ceil_div_ll(long long a, long long b) {  // b > 0
   return a >= 0 ? (a + b - 1) / b : -((-a) / b);
 }
@@ -327,8 +330,9 @@ void dgrad_classes(const Plan& p, size_t esz, std::vector<DgradClassPlan>* out, 
         for (int i = 0; i < 3; ++i) c.dev.W[i] = p.W[i];
         c.dev.gs[2] = 1; c.dev.gs[1] = p.G[2]; c.dev.gs[0] = p.G[1] * p.G[2];
         c.dev.Gp = p.Gp;
-        c.tab_off = off; off += align_up((size_t)c.K * sizeof(TapEntry), 256);
-        c.wp_off = off;  off += align_up((size_t)c.K * p.C * esz, 256);
+        c.tab_off = off; off += align_up((size_t)c.K * sizeof(TapEntry), 1024);
+        // packed filters: [c][(f, tap)] for the cp.async kernels, [c][tap][f padded to 16] for the float64 TMA kernel
+        c.wp_off = off;  off += align_up((size_t)round_up(p.F, 16) * c.ntap * p.C * esz, 1024);
         out->push_back(c);
       }
   *ws_bytes = off;
@@ -348,7 +352,6 @@ bool tc_enabled() {
   return !(e && strcmp(e, "mma") == 0);
 }
 
-inline int round_up(long long v, int m) { return (int)((v + m - 1) / m * m); }
 
 // the tensor-core path wants a GEMM worth its fixed costs: >= 16 input and output channels
 bool tc_eligible(const Plan& p, int which) {
@@ -1389,23 +1392,162 @@ __global__ void __launch_bounds__(256) pool_bwd_planes_kernel(const float* __res
 
 // ---- the three convolutions ------------------------------------------------------------
 
+// ---- FP64 fwd / dgrad with TMA-staged operands (conv_f64_tma.cuh): 0 ok, 1 error, 2 not applicable ----
+// MGB_F64_PATH=cpasync keeps float64 on the cp.async kernels of conv_gemm.cuh (A/B comparisons, tests)
+struct F64Job {
+  const double* src;            // gathered tensor [N][CH][X0][X1][X2]
+  int X[3];                     // its spatial extents
+  long long CH, nbatch;         // its channels (contracted), samples
+  int P[3], pmul[3], base[3];   // pixel grid; source coord = pixel * pmul + base + tap delta
+  int ntaps;
+  short d[f64t::kMaxTaps][3];   // tap coordinate deltas
+  short widx[f64t::kMaxTaps];   // flat filter tap of each tap
+  const double* w;              // filters (F, C, Wp)
+  long long F, C, Wp;
+  int rows_are_f;               // output channels are filters (fwd) or input channels (dgrad)
+  double* out;
+  OutMap om;
+  double* wpack;                // rows x ntaps x chpad doubles of workspace
+};
+
+inline size_t f64_pack_bytes(long long rows, long long ntaps, long long ch) {
+  return align_up((size_t)rows * ntaps * round_up(ch, 16) * sizeof(double), 1024);
+}
+
+// forward workspace of the mma.sync / DMMA path: tap table, then (float64) the packed filters of the TMA kernel
+inline size_t fwd_tab_bytes(const Plan& p) { return align_up((size_t)(p.C * p.Wp) * sizeof(TapEntry), 1024); }
+inline size_t fwd_ws(const Plan& p) {
+  return fwd_tab_bytes(p) + (p.dtype == MGB_F64 ? f64_pack_bytes(p.F, p.Wp, p.C) : 0);
+}
+
+bool f64_tma_enabled() {
+  const char* e = getenv("MGB_F64_PATH");
+  return !(e && strcmp(e, "cpasync") == 0) && tma_enabled();
+}
+
+int f64_fwdlike_tma(const F64Job& j, cudaStream_t st) {
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc || !f64_tma_enabled()) return 2;
+  const long long rows = j.rows_are_f ? j.F : j.C;
+  if (j.ntaps < 1 || j.ntaps > f64t::kMaxTaps || j.CH < 32 || rows < 48) return 2;
+  const int chpad = round_up(j.CH, 16);
+  if ((long long)chpad * 100 > j.CH * 115) return 2;                           // padded channels are wasted DMMAs
+  if (j.X[2] % 2 || ((uintptr_t)j.src & 15) || ((uintptr_t)j.wpack & 1023)) return 2;   // TMA strides are multiples of 16 B
+  for (int i = 0; i < 3; ++i) if (j.pmul[i] > 32 || j.P[i] < 1 || j.X[i] < 1) return 2;
+  if (j.pmul[2] != 1) return 2;          // the aligned 12-pixel box serves shifts of 0 / 1 pixel at stride 1 only
+  const bool wide = rows > 64;                                                   // 128 x 128 tiles, else 256 x 64
+  const int BMt = wide ? 128 : 256;
+  // pixel box: 8 along the last axis, BM / 8 over the other axes and the batch (powers of two), fewest tiles
+  int box[3] = {1, 1, 8}, boxn = 1;
+  long long best = -1;
+  const int rest = BMt / 8;
+  for (int b0 = 1; b0 <= rest; b0 <<= 1)
+    for (int b1 = 1; b0 * b1 <= rest; b1 <<= 1) {
+      const int bn = rest / (b0 * b1);
+      if (b0 * j.pmul[0] > 256 || b1 * j.pmul[1] > 256) continue;
+      const long long tiles = (long long)((j.P[0] + b0 - 1) / b0) * ((j.P[1] + b1 - 1) / b1) * ((j.P[2] + 7) / 8) *
+                              ((j.nbatch + bn - 1) / bn);
+      if (best < 0 || tiles < best) { best = tiles; box[0] = b0; box[1] = b1; boxn = bn; }
+    }
+  const long long pixels = j.nbatch * j.P[0] * j.P[1] * j.P[2];
+  if (best < 0 || best > INT32_MAX || best * BMt * 100 > pixels * 118) return 2;   // ragged tiles would cost more than they save
+  f64t::FwdLikeParams fp;
+  fp.out = j.out; fp.om = j.om;
+  for (int i = 0; i < 3; ++i) {
+    fp.P[i] = j.P[i]; fp.pmul[i] = j.pmul[i]; fp.base[i] = j.base[i]; fp.box[i] = box[i];
+    fp.tiles[i] = (j.P[i] + box[i] - 1) / box[i];
+  }
+  fp.boxn = boxn; fp.tiles_n = (int)((j.nbatch + boxn - 1) / boxn);
+  fp.Nbatch = (int)j.nbatch; fp.Nout = (int)rows; fp.nchunk = chpad / 16;
+  fp.taps.n = j.ntaps;
+  fp.dbg = getenv("MGB_F64_DBG") ? atoi(getenv("MGB_F64_DBG")) : 0;
+  f64t::PackTaps pt;
+  pt.n = j.ntaps;
+  for (int t = 0; t < j.ntaps; ++t) {
+    for (int i = 0; i < 3; ++i) fp.taps.d[t][i] = j.d[t][i];
+    pt.widx[t] = j.widx[t];
+  }
+  const long long Ktot = (long long)j.ntaps * chpad;
+  f64t::pack_w_f64_kernel<<<small_grid(rows * Ktot), 256, 0, st>>>(j.w, j.wpack, (int)j.F, (int)j.C, (int)j.Wp,
+                                                                    j.rows_are_f, chpad, pt);
+  MGB_LAUNCH_CHECK();
+  CUtensorMap ma, mb;
+  {
+    const cuuint64_t xp = (cuuint64_t)j.X[0] * j.X[1] * j.X[2];
+    cuuint64_t dims[5] = {(cuuint64_t)j.X[2], (cuuint64_t)j.CH, (cuuint64_t)j.X[1], (cuuint64_t)j.X[0], (cuuint64_t)j.nbatch};
+    cuuint64_t strides[4] = {xp * 8, (cuuint64_t)j.X[2] * 8, (cuuint64_t)j.X[1] * j.X[2] * 8, (cuuint64_t)j.CH * xp * 8};
+    cuuint32_t bx[5] = {(cuuint32_t)f64t::AW, 16, (cuuint32_t)(box[1] * j.pmul[1]), (cuuint32_t)(box[0] * j.pmul[0]),
+                        (cuuint32_t)boxn};
+    cuuint32_t estr[5] = {1, 1, (cuuint32_t)j.pmul[1], (cuuint32_t)j.pmul[0], 1};
+    if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)j.src, dims, strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 2;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 8};
+    cuuint32_t bx[2] = {16, (cuuint32_t)(wide ? 128 : 64)};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)j.wpack, dims, strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 2;
+  }
+  if (wide) {
+    constexpr int ST = 5;
+    auto kern = f64t::f64_fwdlike_tma_kernel<128, 128, ST>;
+    if (getenv("MGB_F64_NOREALLOC")) kern = f64t::f64_fwdlike_tma_kernel<128, 128, ST, false>;
+    const size_t smem = f64t::fwdlike_smem_bytes<128, 128, ST>();
+    MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)best, (unsigned)((rows + 127) / 128)), f64t::THREADS, smem, st>>>(fp, ma, mb);
+  } else {
+    constexpr int ST = 4;
+    auto kern = f64t::f64_fwdlike_tma_kernel<256, 64, ST>;
+    const size_t smem = f64t::fwdlike_smem_bytes<256, 64, ST>();
+    MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((unsigned)best, (unsigned)((rows + 63) / 64)), f64t::THREADS, smem, st>>>(fp, ma, mb);
+  }
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
+
 template <typename T>
 int fwd_t(const Plan& p, const T* x, const T* w, T* y, void* ws, size_t ws_bytes, cudaStream_t st) {
   long long K = p.C * p.Wp, M = p.N * p.Gp;
   if (M * p.F == 0) return 0;
   if (K == 0) { MGB_CUDA(cudaMemsetAsync(y, 0, (size_t)(M * p.F) * sizeof(T), st)); return 0; }
-  size_t need = (size_t)K * sizeof(TapEntry);
+  size_t need = fwd_ws(p);
   if (ws_bytes < need || !ws) return fail("conv fwd: workspace %zu < %zu bytes", ws_bytes, need);
-  TapEntry* tab = (TapEntry*)ws;
-  build_x_table<<<small_grid(K), 256, 0, st>>>(tab, x_table_args(p));
-  MGB_LAUNCH_CHECK();
   FwdParams<T> fp;
-  fp.src = x; fp.tab = tab; fp.B = w; fp.ldb = K; fp.out = y;
-  fp.ga = geom_x_by_output(p);
   fp.om.sample_stride = p.F * p.Gp; fp.om.chan_stride = p.Gp;
   for (int i = 0; i < 3; ++i) { fp.om.omul[i] = 1; fp.om.obase[i] = 0; }
   fp.om.os[2] = 1; fp.om.os[1] = p.G[2]; fp.om.os[0] = p.G[1] * p.G[2];
+  if constexpr (sizeof(T) == 8) {
+    if (p.Wp <= f64t::kMaxTaps) {           // TMA-staged DMMA kernel first
+      F64Job j;
+      j.src = x; j.CH = p.C; j.nbatch = p.N;
+      for (int i = 0; i < 3; ++i) { j.X[i] = p.X[i]; j.P[i] = p.G[i]; j.pmul[i] = p.S[i]; j.base[i] = -p.Pd[i]; }
+      j.ntaps = (int)p.Wp;
+      for (int t = 0; t < j.ntaps; ++t) {
+        int r = t;
+        const int t2 = r % p.W[2]; r /= p.W[2];
+        const int t1 = r % p.W[1], t0 = r / p.W[1];
+        j.d[t][0] = (short)(t0 * p.D[0]); j.d[t][1] = (short)(t1 * p.D[1]); j.d[t][2] = (short)(t2 * p.D[2]);
+        j.widx[t] = (short)t;
+      }
+      j.w = w; j.F = p.F; j.C = p.C; j.Wp = p.Wp; j.rows_are_f = 1;
+      j.out = y; j.om = fp.om; j.wpack = (double*)((char*)ws + fwd_tab_bytes(p));
+      const int rc = f64_fwdlike_tma(j, st);
+      if (rc != 2) return rc;
+    }
+  }
+  TapEntry* tab = (TapEntry*)ws;
+  build_x_table<<<small_grid(K), 256, 0, st>>>(tab, x_table_args(p));
+  MGB_LAUNCH_CHECK();
+  fp.src = x; fp.tab = tab; fp.B = w; fp.ldb = K; fp.out = y;
+  fp.ga = geom_x_by_output(p);
   fp.M = (int)M; fp.N = (int)p.F; fp.K = (int)K;
+  fp.dbg_noload = getenv("MGB_F64_NOLOAD") ? 1 : 0;
   return run_fwdlike<T>(fp, st);
 }
 
@@ -1423,10 +1565,7 @@ int dgrad_t(const Plan& p, const T* dy, const T* w, T* dx, void* ws, size_t ws_b
   for (auto& c : cls) {
     TapEntry* tab = (TapEntry*)((char*)ws + c.tab_off);
     T* wpack = (T*)((char*)ws + c.wp_off);
-    build_dgrad_class<T><<<small_grid(c.K * (p.C + 1)), 256, 0, st>>>(tab, wpack, w, c.dev);
-    MGB_LAUNCH_CHECK();
     FwdParams<T> fp;
-    fp.src = dy; fp.tab = tab; fp.B = wpack; fp.ldb = c.K; fp.out = dx;
     fp.ga.sample_stride = p.F * p.Gp;
     for (int i = 0; i < 3; ++i) {
       fp.ga.P[i] = c.Q[i]; fp.ga.pmul[i] = 1; fp.ga.base[i] = c.qlo[i]; fp.ga.X[i] = p.G[i];
@@ -1437,6 +1576,29 @@ int dgrad_t(const Plan& p, const T* dy, const T* w, T* dx, void* ws, size_t ws_b
     fp.ga.pp = c.Q[0] * c.Q[1] * c.Q[2];
     fp.om.sample_stride = p.C * p.Xp; fp.om.chan_stride = p.Xp;
     fp.om.os[2] = 1; fp.om.os[1] = p.X[2]; fp.om.os[0] = p.X[1] * p.X[2];
+    if constexpr (sizeof(T) == 8) {
+      if (c.ntap <= f64t::kMaxTaps) {         // TMA-staged DMMA kernel first
+        F64Job j;
+        j.src = dy; j.CH = p.F; j.nbatch = p.N;
+        for (int i = 0; i < 3; ++i) { j.X[i] = p.G[i]; j.P[i] = c.Q[i]; j.pmul[i] = 1; j.base[i] = c.qlo[i]; }
+        j.ntaps = c.ntap;
+        for (int t = 0; t < c.ntap; ++t) {
+          int r = t;
+          const int j2 = r % c.dev.cnt[2]; r /= c.dev.cnt[2];
+          const int j1 = r % c.dev.cnt[1], j0 = r / c.dev.cnt[1];
+          j.d[t][0] = c.dev.e[0][j0]; j.d[t][1] = c.dev.e[1][j1]; j.d[t][2] = c.dev.e[2][j2];
+          j.widx[t] = (short)((c.dev.kidx[0][j0] * p.W[1] + c.dev.kidx[1][j1]) * p.W[2] + c.dev.kidx[2][j2]);
+        }
+        j.w = w; j.F = p.F; j.C = p.C; j.Wp = p.Wp; j.rows_are_f = 0;
+        j.out = dx; j.om = fp.om; j.wpack = (double*)wpack;
+        const int rc = f64_fwdlike_tma(j, st);
+        if (rc == 1) return 1;
+        if (rc == 0) continue;
+      }
+    }
+    build_dgrad_class<T><<<small_grid(c.K * (p.C + 1)), 256, 0, st>>>(tab, wpack, w, c.dev);
+    MGB_LAUNCH_CHECK();
+    fp.src = dy; fp.tab = tab; fp.B = wpack; fp.ldb = c.K; fp.out = dx;
     fp.M = (int)(p.N * fp.ga.pp); fp.N = (int)p.C; fp.K = (int)c.K;
     if (run_fwdlike<T>(fp, st)) return 1;
   }
@@ -1502,7 +1664,7 @@ extern "C" int mgb_conv_workspace_bytes(const mgb_conv_desc* d, int which, size_
   size_t esz = p.dtype == MGB_F32 ? 4 : 8;
   size_t need = 0;
   if (which == 0) {
-    need = tc_eligible(p, 0) ? tc_fwd_ws(p) : (size_t)(p.C * p.Wp) * sizeof(TapEntry);
+    need = tc_eligible(p, 0) ? tc_fwd_ws(p) : fwd_ws(p);
   } else if (which == 1) {
     std::vector<DgradClassPlan> cls;
     dgrad_classes(p, esz, &cls, &need);

@@ -23,7 +23,7 @@ for i in range(nd):
     cd.X[i], cd.W[i] = cfg["x"][2 + i], cfg["w"][2 + i]
     cd.stride[i], cd.pad[i], cd.dil[i] = tup(cfg["stride"])[i], tup(cfg["padding"])[i], tup(cfg["dilation"])[i]
 y = mg.empty((cfg["x"][0], cfg["w"][0], *geo["G"]), dt)
-gy = mg.full(y.shape, 1.0, dt)
+gy = mg.asdevice(np.random.default_rng(2).standard_normal(y.shape).astype(dt))   # seed-2 normal upstream grad
 dx, dw = mg.empty(cfg["x"], dt), mg.empty(cfg["w"], dt)
 wss = []
 for which in range(3):
