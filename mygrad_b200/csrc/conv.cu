@@ -1605,13 +1605,91 @@ int dgrad_t(const Plan& p, const T* dy, const T* w, T* dx, void* ws, size_t ws_b
   return 0;
 }
 
+// ---- FP64 wgrad with TMA-staged operands (conv_f64_tma.cuh) ----
+struct F64WgradPlan {
+  int NB, mt, nt, cblocks, nblocks, tiles1, tiles2, splits;
+  long long boxes, per;
+};
+
+// geometry-only part of the decision (also sizes the workspace): false = not applicable
+bool f64_wgrad_tma_plan(const Plan& p, F64WgradPlan* out) {
+  if (p.dtype != MGB_F64 || p.F < 96 || p.C < 32 || p.S[2] != 1 || p.G[2] % 2 || p.X[2] % 2) return false;
+  if (2 * p.S[1] > 256 || p.N * p.Gp == 0) return false;
+  F64WgradPlan w;
+  w.cblocks = (int)((p.C + 31) / 32);
+  if ((long long)w.cblocks * 32 * 100 > p.C * 115) return false;               // padded channels are wasted DMMAs
+  w.nblocks = (int)p.Wp * w.cblocks;
+  const int pad3 = (w.nblocks + 2) / 3 * 3, pad4 = (w.nblocks + 3) / 4 * 4;
+  w.NB = pad3 < pad4 ? 3 : 4;
+  if ((long long)std::min(pad3, pad4) * 100 > (long long)w.nblocks * 125) return false;
+  w.tiles1 = (p.G[1] + 1) / 2; w.tiles2 = (p.G[2] + 7) / 8;
+  w.boxes = (long long)p.N * p.G[0] * w.tiles1 * w.tiles2;
+  if (w.boxes > INT32_MAX || w.boxes * 16 * 100 > p.N * p.Gp * 120) return false;   // ragged 2 x 8 boxes
+  w.mt = (int)((p.F + 127) / 128); w.nt = (w.nblocks + w.NB - 1) / w.NB;
+  int splits = (int)std::max<long long>(1, std::min<long long>(std::max(1, sm_count() / (w.mt * w.nt)), w.boxes / 8));
+  w.per = (w.boxes + splits - 1) / splits;
+  w.splits = (int)((w.boxes + w.per - 1) / w.per);
+  *out = w;
+  return true;
+}
+
+// returns 0 ok (sets *splits), 1 error, 2 not applicable
+int f64_wgrad_tma(const Plan& p, const double* dy, const double* x, double* partial, int* splits, cudaStream_t st) {
+  EncodeTiledFn enc = tma_encoder();
+  F64WgradPlan w;
+  if (!enc || !f64_tma_enabled() || !f64_wgrad_tma_plan(p, &w)) return 2;
+  if (((uintptr_t)dy & 15) || ((uintptr_t)x & 15)) return 2;
+  CUtensorMap mdy, mx;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)p.G[2], (cuuint64_t)p.G[1], (cuuint64_t)p.G[0], (cuuint64_t)p.F, (cuuint64_t)p.N};
+    cuuint64_t strides[4] = {(cuuint64_t)p.G[2] * 8, (cuuint64_t)p.G[1] * p.G[2] * 8, (cuuint64_t)p.Gp * 8, (cuuint64_t)p.F * p.Gp * 8};
+    cuuint32_t bx[5] = {8, 2, 1, 128, 1}, estr[5] = {1, 1, 1, 1, 1};
+    if (enc(&mdy, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)dy, dims, strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 2;
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)p.X[2], (cuuint64_t)p.X[1], (cuuint64_t)p.X[0], (cuuint64_t)p.C, (cuuint64_t)p.N};
+    cuuint64_t strides[4] = {(cuuint64_t)p.X[2] * 8, (cuuint64_t)p.X[1] * p.X[2] * 8, (cuuint64_t)p.Xp * 8, (cuuint64_t)p.C * p.Xp * 8};
+    cuuint32_t bx[5] = {(cuuint32_t)f64t::WX, (cuuint32_t)(2 * p.S[1]), 1, 32, 1}, estr[5] = {1, (cuuint32_t)p.S[1], 1, 1, 1};
+    if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)x, dims, strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 2;
+  }
+  f64t::WgradParams wp;
+  wp.partial = partial;
+  for (int i = 0; i < 3; ++i) { wp.G[i] = p.G[i]; wp.S[i] = p.S[i]; wp.Pd[i] = p.Pd[i]; wp.D[i] = p.D[i]; wp.W[i] = p.W[i]; }
+  wp.F = (int)p.F; wp.C = (int)p.C; wp.Wp = (int)p.Wp; wp.cblocks = w.cblocks; wp.nblocks_total = w.nblocks;
+  wp.tiles1 = w.tiles1; wp.tiles2 = w.tiles2;
+  wp.boxes_total = (int)w.boxes; wp.boxes_per_split = (int)w.per;
+  constexpr int ST = 4;
+  const dim3 grid(w.mt, w.nt, w.splits);
+  if (w.NB == 3) {
+    auto kern = f64t::f64_wgrad_tma_kernel<3, ST>;
+    const size_t smem = f64t::wgrad_smem_bytes<3, ST>();
+    MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, f64t::THREADS, smem, st>>>(wp, mdy, mx);
+  } else {
+    auto kern = f64t::f64_wgrad_tma_kernel<4, ST>;
+    const size_t smem = f64t::wgrad_smem_bytes<4, ST>();
+    MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, f64t::THREADS, smem, st>>>(wp, mdy, mx);
+  }
+  MGB_LAUNCH_CHECK();
+  *splits = w.splits;
+  return 0;
+}
+
 template <typename T>
 size_t wgrad_ws(const Plan& p, int* splits, int* kps) {
   int M = (int)p.F, N = (int)(p.C * p.Wp), K = (int)(p.N * p.Gp);
   wgrad_plan<T>(M, N, K, splits, kps);
   size_t off = align_up((size_t)M * sizeof(TapEntry), 256);
   off += align_up((size_t)N * sizeof(TapEntry), 256);
-  off += (size_t)(*splits) * M * N * sizeof(T);
+  int slabs = *splits;
+  F64WgradPlan w;
+  if (sizeof(T) == 8 && f64_wgrad_tma_plan(p, &w)) slabs = std::max(slabs, w.splits);
+  off += (size_t)slabs * M * N * sizeof(T);
   return off;
 }
 
@@ -1630,6 +1708,12 @@ int wgrad_t(const Plan& p, const T* dy, const T* x, T* dw, void* ws, size_t ws_b
   TapEntry* tabA = (TapEntry*)ws;
   TapEntry* tabB = (TapEntry*)((char*)ws + align_up((size_t)M * sizeof(TapEntry), 256));
   T* partial = (T*)((char*)tabB + align_up((size_t)N * sizeof(TapEntry), 256));
+  if constexpr (sizeof(T) == 8) {        // TMA-staged DMMA kernel first
+    int s2 = 0;
+    const int rc = f64_wgrad_tma(p, dy, x, partial, &s2, st);
+    if (rc == 1) return 1;
+    if (rc == 0) return finish_dw<T>(partial, dw, (long long)M * N, s2, st);
+  }
   build_chan_table<<<small_grid(M), 256, 0, st>>>(tabA, M, p.Gp);
   MGB_LAUNCH_CHECK();
   build_x_table<<<small_grid(N), 256, 0, st>>>(tabB, x_table_args(p));

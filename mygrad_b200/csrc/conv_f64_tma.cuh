@@ -193,6 +193,171 @@ f64_fwdlike_tma_kernel(const __grid_constant__ FwdLikeParams p, const __grid_con
   }
 }
 
+// ---- wgrad: D[f, (tap, c)] = sum over pixels of dy[pixel, f] * x[pixel * s + tap * d - p, c] ----
+//
+// K walks the output pixels 16 at a time (2 rows x 8 pixels of one image), split over CTAs.  Per k-slab the
+// producer brings dy as [128 filters][2 rows][8 pixels] under SWIZZLE_128B — TMA gives every 64-byte inner row
+// its own 128-byte line (measured: scripts/probes/tma_f64_probe.cu variant 9), so the slab occupies 32 KB
+// for 16 KB of data and line (2 f + row) holds chunk c at 16-byte slot c ^ (line & 7): 8 filters x 4 k of an
+// A fragment land on all banks exactly twice — and, for each of the
+// N tile's (tap, 32-channel) blocks, x as [32 channels][2 rows][WX pixels]: WX = 10 because the tap shifts
+// the start by single pixels and TMA wants it even (see above); 160-byte rows put the 8 columns x 4 k of
+// a B fragment on all banks exactly twice.  Conv strides along the outer axes are the map's traversal
+// strides; the innermost axis must have stride 1.
+constexpr int WX = 10;
+constexpr int WG_A_BYTES = 128 * BK * 8;             // dy slab: bytes TMA delivers
+constexpr int WG_A_STAGE = 2 * WG_A_BYTES;           // ... and its footprint (64-byte rows in 128-byte lines)
+constexpr int WG_BLK = 32 * 2 * WX * 8;              // one (tap, 32-channel) block of x
+
+struct WgradParams {
+  double* partial;             // [splits][F][C][Wp]
+  int G[3];                    // output extents
+  int S[3], Pd[3], D[3], W[3];
+  int F, C, Wp, cblocks, nblocks_total;
+  int tiles1, tiles2;          // ceil(G1 / 2), ceil(G2 / 8)
+  int boxes_total, boxes_per_split;
+};
+
+template <int NB, int STAGES>
+constexpr size_t wgrad_smem_bytes() {
+  return (size_t)STAGES * (WG_A_STAGE + NB * WG_BLK) + 1024 + 256;
+}
+
+// grid = (ceil(F / 128), ceil(nblocks / NB), splits); NB = 3 or 4 blocks of 32 columns per N tile
+template <int NB, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1)
+f64_wgrad_tma_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUtensorMap map_dy,
+                     const __grid_constant__ CUtensorMap map_x) {
+  constexpr int BN = NB * 32, WN = BN / 4, NI = WN / 8;          // 8 MMA warps: 2 (M) x 4 (N), 64 x WN each
+  constexpr int STAGE = WG_A_STAGE + NB * WG_BLK;
+  static_assert(STAGE % 1024 == 0, "swizzled dy slabs start 1024-byte aligned");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma::prefetch_tmap(&map_dy); tma::prefetch_tmap(&map_x);
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(full_bar + s, 1);
+      tc::mbar_init(empty_bar + s, CONSUMERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  const int m0 = blockIdx.x * 128;
+  const int blk0 = blockIdx.y * NB;
+  const int nvalid = min(NB, p.nblocks_total - blk0);
+  const int kb0 = blockIdx.z * p.boxes_per_split;
+  const int kb1 = min(p.boxes_total, kb0 + p.boxes_per_split);
+  const int S = max(0, kb1 - kb0);
+
+  // tap of block b -> coordinate deltas
+  auto tap_delta = [&](int blk, int& d0, int& d1, int& d2, int& cb) {
+    int tap = blk / p.cblocks;
+    cb = blk - tap * p.cblocks;
+    const int t2 = tap % p.W[2]; tap /= p.W[2];
+    const int t1 = tap % p.W[1], t0 = tap / p.W[1];
+    d0 = t0 * p.D[0] - p.Pd[0]; d1 = t1 * p.D[1] - p.Pd[1]; d2 = t2 * p.D[2] - p.Pd[2];
+  };
+
+  if (warp >= CONSUMERS) {
+    reg_dealloc<40>();
+    if (warp == CONSUMERS && tc::elect_one()) {
+      // ===== producer =====
+      int bd0[NB], bd1[NB], bd2[NB], bcb[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) tap_delta(min(blk0 + b, p.nblocks_total - 1), bd0[b], bd1[b], bd2[b], bcb[b]);
+      const uint32_t tx = (uint32_t)(WG_A_BYTES + nvalid * WG_BLK);
+      for (int s = 0; s < S; ++s) {
+        const int stage = s % STAGES;
+        if (s >= STAGES) tc::mbar_wait(empty_bar + stage, (uint32_t)((s / STAGES - 1) & 1));
+        int kb = kb0 + s;
+        const int t2 = kb % p.tiles2; kb /= p.tiles2;
+        const int t1 = kb % p.tiles1; kb /= p.tiles1;
+        const int g0 = kb % p.G[0];
+        const int n = kb / p.G[0];
+        const int g1 = t1 * 2, g2 = t2 * 8;
+        const uint32_t a_dst = tc::smem_u32(smem + stage * STAGE);
+        tma::mbar_expect_tx(full_bar + stage, tx);
+        tma::tma_load_5d(a_dst, &map_dy, full_bar + stage, g2, g1, g0, m0, n);
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+          if (b < nvalid)
+            tma::tma_load_5d(a_dst + WG_A_STAGE + b * WG_BLK, &map_x, full_bar + stage, (g2 * p.S[2] + bd2[b]) & ~1,
+                             g1 * p.S[1] + bd1[b], g0 * p.S[0] + bd0[b], bcb[b] * 32, n);
+      }
+    }
+    return;
+  }
+
+  // ===== MMA warps =====
+  reg_alloc<224>();
+  const int warp_m = (warp & 1) * 64, warp_n = (warp >> 1) * WN;
+  const int lr = lane >> 2, lk = lane & 3;
+  double acc[8][NI][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  int a_off[8];                 // bytes; the row's line and the swizzled 16-byte slot are added per kk
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a_off[i] = (warp_m + i * 8 + lr) * 256 + (lk & 1) * 8;
+  int b_off[NI];                // bytes: column row + the block's odd-start shift + lk
+#pragma unroll
+  for (int j = 0; j < NI; ++j) {
+    const int col = warp_n + j * 8;
+    int d0, d1, d2, cb;
+    tap_delta(min(blk0 + col / 32, p.nblocks_total - 1), d0, d1, d2, cb);
+    b_off[j] = WG_A_STAGE + (col + lr) * (2 * WX * 8) + ((d2 & 1) + lk) * 8;      // g2 * S2 is even (S2 == 1, g2 % 8 == 0)
+  }
+
+  for (int s = 0; s < S; ++s) {
+    const int stage = s % STAGES;
+    tc::mbar_wait(full_bar + stage, (uint32_t)((s / STAGES) & 1));
+    const uint8_t* st = smem + stage * STAGE;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[8], b[NI];
+      const int row = kk >> 1;                                   // k = kk * 4 + lk -> (row, column) of the 2 x 8 box
+      const int chunk = row * 128 + (((2 * (kk & 1) + (lk >> 1)) ^ ((lr & 3) * 2 + row)) << 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const double*>(st + a_off[i] + chunk);
+      const int koff = (row * WX + (kk & 1) * 4) * 8;
+#pragma unroll
+      for (int j = 0; j < NI; ++j) b[j] = *reinterpret_cast<const double*>(st + b_off[j] + koff);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) dmma(acc[i][j], a[i], b[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar + stage);
+  }
+
+  // epilogue: partial[split][f][c][tap]
+  double* out = p.partial + (long long)blockIdx.z * p.F * p.C * p.Wp;
+  const int lc = (lane & 3) * 2;
+#pragma unroll
+  for (int j = 0; j < NI; ++j) {
+    const int col = warp_n + j * 8 + lc;          // even: col and col + 1 share a block
+    const int blk = blk0 + col / 32;
+    if (blk >= p.nblocks_total) continue;
+    const int tap = blk / p.cblocks, cb = blk - tap * p.cblocks;
+    const int c = cb * 32 + (col & 31);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = m0 + warp_m + i * 8 + lr;
+      if (f >= p.F) continue;
+      if (c < p.C) out[((long long)f * p.C + c) * p.Wp + tap] = acc[i][j][0];
+      if (c + 1 < p.C) out[((long long)f * p.C + c + 1) * p.Wp + tap] = acc[i][j][1];
+    }
+  }
+}
+
 // packed filters for the kernel above: out[row][tap][ch] (ch padded to a multiple of 16 with zeros)
 //   rows_are_f = 1 (forward): row = f, ch = c;   0 (dgrad): row = c, ch = f
 struct PackTaps {

@@ -58,11 +58,12 @@ int main(int argc, char** argv) {
     case 6: rank = 3; set(0, X2, 0, 8); set(1, X1, X2 * 8, 8); set(2, C, xp * 8, 16); break;
     case 7: rank = 3; set(0, X2, 0, 16); set(1, C, xp * 8, 16); set(2, X1, X2 * 8, 8); break;   // inner 128 B
     case 8: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; rank = 3; set(0, 2 * X2, 0, 16); set(1, C, xp * 8, 16); set(2, X1, X2 * 8, 8); break;  // same bytes as 5, as float32
+    case 9: rank = 3; set(0, X2, 0, 8); set(1, X1, X2 * 8, 2); set(2, C, xp * 8, 16); break;   // [c][2][8] under SWIZZLE_128B
     default: return 2;
   }
   bytes = 8; for (int i = 0; i < rank; ++i) bytes *= box[i];
   if (dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32) bytes /= 2;
-  r = cuTensorMapEncodeTiled(&m, dt, rank, d, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+  r = cuTensorMapEncodeTiled(&m, dt, rank, d, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, v == 9 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   printf("variant %d rank %d encode rc %d bytes %d\n", v, rank, (int)r, bytes);
   if (r) return 1;
@@ -74,5 +75,11 @@ int main(int argc, char** argv) {
   std::vector<double> o(8192);
   cudaMemcpy(o.data(), out, 65536, cudaMemcpyDeviceToHost);
   printf("variant %d: %s; smem[0..3]=%g %g %g %g smem[8..9]=%g %g\n", v, cudaGetErrorString(e), o[0], o[1], o[2], o[3], o[8], o[9]);
+  if (v == 9)
+    for (int row = 0; row < 10; ++row) {
+      printf("row %2d:", row);
+      for (int i = 0; i < 16; ++i) printf(" %4g", o[row * 16 + i]);
+      printf("\n");
+    }
   return e != cudaSuccess;
 }
