@@ -1460,7 +1460,6 @@ int f64_fwdlike_tma(const F64Job& j, cudaStream_t st) {
   fp.boxn = boxn; fp.tiles_n = (int)((j.nbatch + boxn - 1) / boxn);
   fp.Nbatch = (int)j.nbatch; fp.Nout = (int)rows; fp.nchunk = chpad / 16;
   fp.taps.n = j.ntaps;
-  fp.dbg = getenv("MGB_F64_DBG") ? atoi(getenv("MGB_F64_DBG")) : 0;
   f64t::PackTaps pt;
   pt.n = j.ntaps;
   for (int t = 0; t < j.ntaps; ++t) {
@@ -1495,7 +1494,6 @@ int f64_fwdlike_tma(const F64Job& j, cudaStream_t st) {
   if (wide) {
     constexpr int ST = 5;
     auto kern = f64t::f64_fwdlike_tma_kernel<128, 128, ST>;
-    if (getenv("MGB_F64_NOREALLOC")) kern = f64t::f64_fwdlike_tma_kernel<128, 128, ST, false>;
     const size_t smem = f64t::fwdlike_smem_bytes<128, 128, ST>();
     MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((unsigned)best, (unsigned)((rows + 127) / 128)), f64t::THREADS, smem, st>>>(fp, ma, mb);
@@ -1547,7 +1545,6 @@ int fwd_t(const Plan& p, const T* x, const T* w, T* y, void* ws, size_t ws_bytes
   fp.src = x; fp.tab = tab; fp.B = w; fp.ldb = K; fp.out = y;
   fp.ga = geom_x_by_output(p);
   fp.M = (int)M; fp.N = (int)p.F; fp.K = (int)K;
-  fp.dbg_noload = getenv("MGB_F64_NOLOAD") ? 1 : 0;
   return run_fwdlike<T>(fp, st);
 }
 

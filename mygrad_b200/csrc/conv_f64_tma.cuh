@@ -5,7 +5,7 @@
 // those warps execute ~4.7 other instructions (tap-table look-ups, bounds checks, address arithmetic),
 // every k-slab ends in a __syncthreads, and the DMMA pipe idles a quarter of the time (ncu: 74.7 % active
 // at C2; with the main-loop copies removed the same kernel runs 4.31 -> 3.67 ms).  Here
-//   * one elected thread of a ninth warp feeds the ring: per 16-deep k-slab ONE cp.async.bulk.tensor.5d
+//   * one elected thread of a producer warpgroup feeds the ring: per 16-deep k-slab ONE cp.async.bulk.tensor.5d
 //     for the pixel operand (a box of BM pixels x 16 channels of one filter tap; tap offsets are
 //     coordinate offsets, the conv stride is the map's traversal stride, padding is TMA zero fill) and
 //     one 2-D TMA for the packed filter matrix, completing on an mbarrier;
@@ -51,7 +51,6 @@ struct FwdLikeParams {
   int tiles[3], tiles_n;
   int Nbatch, Nout;
   int nchunk;                  // 16-channel chunks per tap
-  int dbg;                     // diagnostics: bit 0 = skip the A load, bit 1 = skip the B load
   Taps taps;
 };
 
@@ -72,7 +71,7 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 
 // D[pixel, channel] = sum_{tap, c} T[pixel * pmul + base + delta(tap), c] * B[channel][tap][c]
 // grid = (M tiles, ceil(Nout / BN)); 8 MMA warps of 64 x 32 + a producer warpgroup
-template <int BM, int BN, int STAGES, bool REALLOC = true>
+template <int BM, int BN, int STAGES>
 __global__ void __launch_bounds__(THREADS, 1)
 f64_fwdlike_tma_kernel(const __grid_constant__ FwdLikeParams p, const __grid_constant__ CUtensorMap map_a,
                        const __grid_constant__ CUtensorMap map_b) {
@@ -107,7 +106,7 @@ f64_fwdlike_tma_kernel(const __grid_constant__ FwdLikeParams p, const __grid_con
   const int S = p.taps.n * p.nchunk;
 
   if (warp >= CONSUMERS) {
-    if (REALLOC) reg_dealloc<40>();
+    reg_dealloc<40>();
     if (warp == CONSUMERS && tc::elect_one()) {
       // ===== producer =====
       const int x0 = g0 * p.pmul[0] + p.base[0], x1 = g1 * p.pmul[1] + p.base[1], x2 = g2 + p.base[2];
@@ -115,11 +114,9 @@ f64_fwdlike_tma_kernel(const __grid_constant__ FwdLikeParams p, const __grid_con
       for (int s = 0; s < S; ++s) {
         const int stage = s % STAGES;
         if (s >= STAGES) tc::mbar_wait(empty_bar + stage, (uint32_t)((s / STAGES - 1) & 1));
-        tma::mbar_expect_tx(full_bar + stage, (uint32_t)(((p.dbg & 1) ? 0 : A_STAGE) + ((p.dbg & 2) ? 0 : B_STAGE)));
-        if (!(p.dbg & 1))
+        tma::mbar_expect_tx(full_bar + stage, (uint32_t)(A_STAGE + B_STAGE));
         tma::tma_load_5d(tc::smem_u32(a_ring + stage * A_STAGE), &map_a, full_bar + stage,
                          (x2 + p.taps.d[tap][2]) & ~1, cc * BK, x1 + p.taps.d[tap][1], x0 + p.taps.d[tap][0], n0);
-        if (!(p.dbg & 2))
         tma::tma_load_2d(tc::smem_u32(b_ring + stage * B_STAGE), &map_b, full_bar + stage, s * BK, col0);
         if (++cc == p.nchunk) { cc = 0; ++tap; }
       }
@@ -128,7 +125,7 @@ f64_fwdlike_tma_kernel(const __grid_constant__ FwdLikeParams p, const __grid_con
   }
 
   // ===== MMA warps =====
-  if (REALLOC) reg_alloc<224>();
+  reg_alloc<224>();
   const int warp_m = (warp % (BM / 64)) * 64, warp_n = (warp / (BM / 64)) * 32;
   const int lr = lane >> 2, lk = lane & 3;
   double acc[8][4][2];

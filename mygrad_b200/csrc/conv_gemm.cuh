@@ -48,7 +48,6 @@ struct FwdParams {
   GatherGeom ga;
   OutMap om;
   int M, N, K;
-  int dbg_noload = 0;       // diagnostic (MGB_F64_NOLOAD): skip the main-loop copies — the MMA loop alone
 };
 
 template <typename T>
@@ -348,7 +347,7 @@ conv_fwdlike_kernel(const __grid_constant__ FwdParams<T> p) {
     const int stage = kt % C::STAGES;
     mma_slab<T, C, true>(As + stage * C::A_STAGE_M, Bs + stage * C::B_STAGE, accf, accd, warp_m,
                          warp_n, lane, [&](int part) {
-                           if (more && !p.dbg_noload) load_tile(nk % C::STAGES, nk, part);
+                           if (more) load_tile(nk % C::STAGES, nk, part);
                          });
     cp_async_commit();
   }

@@ -250,6 +250,73 @@ def test_conv_f32_paths_vs_oracle(case, path, monkeypatch):
                  err_msg=f"{path} dw {case}")
 
 
+F64_CASES = [
+    # N, C, F, X, W, stride, padding, dilation  (float64; wide enough for the TMA-fed DMMA kernels)
+    (2, 64, 128, (16, 16), (3, 3), 1, 1, 1),            # C2 in small: 128 x 128 tiles, 96-wide wgrad tiles
+    (3, 32, 96, (14, 24), (3, 3), 1, 1, 1),             # ragged filter tile, ragged pixel boxes
+    (2, 48, 64, (12, 16), (3, 3), 1, 1, 1),             # 64 filters: 256 x 64 tiles forward, wgrad stays on cp.async
+    (2, 64, 128, (17, 16), (3, 3), (2, 1), (1, 1), 1),  # stride 2 on the middle axis (TMA traversal stride); odd rows
+    (2, 64, 100, (12, 18), (2, 3), 1, (0, 2), (1, 2)),  # dilation 2 along the last axis: even shifts only
+    (2, 32, 128, (20, 20), (5, 5), 1, 2, 1),            # 25 taps
+    (2, 64, 128, (16, 16), (3, 3), 2, 1, 1),            # stride 2 everywhere: forward falls back, dgrad classes use TMA
+    (1, 32, 96, (5, 8, 12), (2, 3, 3), (1, 1, 1), (0, 1, 1), 1),   # 3-D
+    (2, 64, 128, (15, 15), (3, 3), 1, 1, 1),            # odd row length: byte strides not multiples of 16, no TMA at all
+    (2, 64, 128, (40,), (5,), 1, 2, 1),                 # 1-D
+]
+
+
+@pytest.mark.parametrize("case", F64_CASES, ids=lambda c: "x".join(map(str, c[:3])) + f"_{len(c[3])}d")
+@pytest.mark.parametrize("path", ["tma", "cpasync"])
+def test_conv_f64_paths_vs_oracle(case, path, monkeypatch):
+    """both float64 kernel families (DMMA fed by TMA with a producer warp, DMMA fed by cp.async) against the
+    oracle at rtol 1e-10; shapes the TMA kernels decline run the cp.async kernels in both settings"""
+    monkeypatch.setenv("MGB_F64_PATH", path)
+    N, C, F, X, W, s, p, d = case
+    rng = np.random.default_rng(hash(case) % (2 ** 32))
+    x = rng.standard_normal((N, C, *X))
+    w = rng.standard_normal((F, C, *W))
+    xt, wt = Tensor(x), Tensor(w)
+    y = conv_nd(xt, wt, stride=s, padding=p, dilation=d)
+    want = oc.conv_fwd(x, w, s, p, d)
+    assert y.shape == want.shape
+    assert_close(y.numpy(), want, np.float64, err_msg=f"{path} fwd {case}")
+    g = rng.standard_normal(want.shape)
+    y.backward(g)
+    assert_close(xt.grad.get(), oc.conv_dx(g, x.shape, w, s, p, d), np.float64, err_msg=f"{path} dx {case}")
+    assert_close(wt.grad.get(), oc.conv_dw(g, x, w.shape, s, p, d), np.float64, err_msg=f"{path} dw {case}")
+
+
+WGRAD_ROWS_CASES = [
+    # shapes for the row-halo wgrad kernel (conv_wgrad2.cuh): box shapes, c-block groups, dilation, strides, 3-D
+    (4, 64, 128, (20, 20), (3, 3), 1, 1, 1),
+    (3, 32, 64, (17, 19), (3, 3), 1, 1, 1),
+    (2, 128, 256, (12, 12), (2, 2), 1, 0, 1),
+    (2, 256, 96, (9, 9), (3, 3), (1, 2), 1, 1),
+    (5, 16, 32, (30, 30), (5, 5), 1, 2, 2),
+    (3, 64, 128, (9, 70), (3, 3), 1, 1, 1),
+    (2, 32, 64, (6, 10, 10), (3, 3, 3), 1, 0, 1),
+    (2, 64, 128, (6, 9, 12), (2, 3, 3), (2, 1, 1), (0, 1, 1), 1),
+    (2, 64, 128, (40,), (5,), 1, 2, 1),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_ROWS_CASES, ids=lambda c: "x".join(map(str, c[:3])) + f"_{len(c[3])}d")
+@pytest.mark.parametrize("rows", ["1", "0"])
+def test_wgrad_row_halo_vs_oracle(case, rows, monkeypatch):
+    """float32 dW from the row-halo kernel (forced wherever legal) and from the per-tap TMA kernel"""
+    monkeypatch.setenv("MGB_WGRAD_ROWS", rows)
+    N, C, F, X, W, s, p, d = case
+    rng = np.random.default_rng(hash(case) % (2 ** 32))
+    x = rng.standard_normal((N, C, *X)).astype(np.float32)
+    w = rng.standard_normal((F, C, *W)).astype(np.float32)
+    xt, wt = Tensor(x, constant=True), Tensor(w)
+    y = conv_nd(xt, wt, stride=s, padding=p, dilation=d)
+    g = rng.standard_normal(y.shape).astype(np.float32)
+    y.backward(g)
+    want = oc.conv_dw(g.astype(np.float64), x.astype(np.float64), w.shape, s, p, d)
+    assert_close(wt.grad.get(), want, np.float32, err_msg=f"rows={rows} dw {case}")
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_pool_random_vs_oracle_bit_exact(dtype):
     rng = np.random.default_rng(77)
