@@ -332,7 +332,7 @@ void dgrad_classes(const Plan& p, size_t esz, std::vector<DgradClassPlan>* out, 
         c.dev.Gp = p.Gp;
         c.tab_off = off; off += align_up((size_t)c.K * sizeof(TapEntry), 1024);
         // packed filters: [c][(f, tap)] for the cp.async kernels, [c][tap][f padded to 16] for the float64 TMA kernel
-        c.wp_off = off;  off += align_up((size_t)round_up(p.F, 16) * c.ntap * p.C * esz, 1024);
+        c.wp_off = off;  off += align_up((size_t)round_up(p.F, 16) * c.ntap * p.C * esz, 1024) + 1024;
         out->push_back(c);
       }
   *ws_bytes = off;
@@ -1416,9 +1416,10 @@ inline size_t f64_pack_bytes(long long rows, long long ntaps, long long ch) {
 
 // forward workspace of the mma.sync / DMMA path: tap table, then (float64) the packed filters of the TMA kernel
 inline size_t fwd_tab_bytes(const Plan& p) { return align_up((size_t)(p.C * p.Wp) * sizeof(TapEntry), 1024); }
-inline size_t fwd_ws(const Plan& p) {
-  return fwd_tab_bytes(p) + (p.dtype == MGB_F64 ? f64_pack_bytes(p.F, p.Wp, p.C) : 0);
+inline size_t fwd_ws(const Plan& p) {   // + 1024: the packed filters start at the next 1024-byte boundary of whatever buffer arrives
+  return fwd_tab_bytes(p) + (p.dtype == MGB_F64 ? f64_pack_bytes(p.F, p.Wp, p.C) + 1024 : 0);
 }
+inline double* align1024(void* ptr) { return (double*)(((uintptr_t)ptr + 1023) & ~(uintptr_t)1023); }
 
 bool f64_tma_enabled() {
   const char* e = getenv("MGB_F64_PATH");
@@ -1534,7 +1535,7 @@ int fwd_t(const Plan& p, const T* x, const T* w, T* y, void* ws, size_t ws_bytes
         j.widx[t] = (short)t;
       }
       j.w = w; j.F = p.F; j.C = p.C; j.Wp = p.Wp; j.rows_are_f = 1;
-      j.out = y; j.om = fp.om; j.wpack = (double*)((char*)ws + fwd_tab_bytes(p));
+      j.out = y; j.om = fp.om; j.wpack = align1024((char*)ws + fwd_tab_bytes(p));
       const int rc = f64_fwdlike_tma(j, st);
       if (rc != 2) return rc;
     }
@@ -1587,7 +1588,7 @@ int dgrad_t(const Plan& p, const T* dy, const T* w, T* dx, void* ws, size_t ws_b
           j.widx[t] = (short)((c.dev.kidx[0][j0] * p.W[1] + c.dev.kidx[1][j1]) * p.W[2] + c.dev.kidx[2][j2]);
         }
         j.w = w; j.F = p.F; j.C = p.C; j.Wp = p.Wp; j.rows_are_f = 0;
-        j.out = dx; j.om = fp.om; j.wpack = (double*)wpack;
+        j.out = dx; j.om = fp.om; j.wpack = align1024(wpack);
         const int rc = f64_fwdlike_tma(j, st);
         if (rc == 1) return 1;
         if (rc == 0) continue;

@@ -258,7 +258,7 @@ F64_CASES = [
     (2, 64, 128, (17, 16), (3, 3), (2, 1), (1, 1), 1),  # stride 2 on the middle axis (TMA traversal stride); odd rows
     (2, 64, 100, (12, 18), (2, 3), 1, (0, 2), (1, 2)),  # dilation 2 along the last axis: even shifts only
     (2, 32, 128, (20, 20), (5, 5), 1, 2, 1),            # 25 taps
-    (2, 64, 128, (16, 16), (3, 3), 2, 1, 1),            # stride 2 everywhere: forward falls back, dgrad classes use TMA
+    (2, 64, 128, (17, 16), (3, 2), 2, (1, 0), 1),       # stride 2 everywhere: forward falls back, dgrad classes use TMA
     (1, 32, 96, (5, 8, 12), (2, 3, 3), (1, 1, 1), (0, 1, 1), 1),   # 3-D
     (2, 64, 128, (15, 15), (3, 3), 1, 1, 1),            # odd row length: byte strides not multiples of 16, no TMA at all
     (2, 64, 128, (40,), (5,), 1, 2, 1),                 # 1-D
