@@ -1408,7 +1408,28 @@ struct F64Job {
   double* out;
   OutMap om;
   double* wpack;                // rows x ntaps x chpad doubles of workspace
+  int pitch2 = 0;               // row length of src in elements (0: X[2]); even — see f64_pitched
 };
+
+// TMA wants every global stride a multiple of 16 bytes: a float64 tensor with an odd innermost extent is first
+// copied to rows one element longer (the extra element is never read: the map's extent stays X2)
+inline int f64_pitch(int X2) { return X2 + (X2 & 1); }
+inline size_t f64_pitched_bytes(long long rows, int X2) {
+  return (X2 & 1) ? align_up((size_t)rows * f64_pitch(X2) * sizeof(double), 1024) + 1024 : 0;
+}
+__global__ void pitch_rows_f64_kernel(const double* __restrict__ src, double* __restrict__ dst, long long rows, int X2,
+                                      int X2p) {
+  const long long total = rows * X2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / X2;
+    dst[r * X2p + (i - r * X2)] = src[i];
+  }
+}
+int f64_pitch_copy(const double* src, double* dst, long long rows, int X2, cudaStream_t st) {
+  pitch_rows_f64_kernel<<<small_grid(rows * X2), 256, 0, st>>>(src, dst, rows, X2, f64_pitch(X2));
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
 
 inline size_t f64_pack_bytes(long long rows, long long ntaps, long long ch) {
   return align_up((size_t)rows * ntaps * round_up(ch, 16) * sizeof(double), 1024);
@@ -1417,7 +1438,8 @@ inline size_t f64_pack_bytes(long long rows, long long ntaps, long long ch) {
 // forward workspace of the mma.sync / DMMA path: tap table, then (float64) the packed filters of the TMA kernel
 inline size_t fwd_tab_bytes(const Plan& p) { return align_up((size_t)(p.C * p.Wp) * sizeof(TapEntry), 1024); }
 inline size_t fwd_ws(const Plan& p) {   // + 1024: the packed filters start at the next 1024-byte boundary of whatever buffer arrives
-  return fwd_tab_bytes(p) + (p.dtype == MGB_F64 ? f64_pack_bytes(p.F, p.Wp, p.C) + 1024 : 0);
+  return fwd_tab_bytes(p) + (p.dtype == MGB_F64 ? f64_pack_bytes(p.F, p.Wp, p.C) + 1024 +
+                                                      f64_pitched_bytes(p.N * p.C * p.X[0] * p.X[1], p.X[2]) : 0);
 }
 inline double* align1024(void* ptr) { return (double*)(((uintptr_t)ptr + 1023) & ~(uintptr_t)1023); }
 
@@ -1426,16 +1448,18 @@ bool f64_tma_enabled() {
   return !(e && strcmp(e, "cpasync") == 0) && tma_enabled();
 }
 
-int f64_fwdlike_tma(const F64Job& j, cudaStream_t st) {
+// dry: decide only (0 = would run)
+int f64_fwdlike_tma(const F64Job& j, cudaStream_t st, bool dry = false) {
   EncodeTiledFn enc = tma_encoder();
   if (!enc || !f64_tma_enabled()) return 2;
   const long long rows = j.rows_are_f ? j.F : j.C;
   if (j.ntaps < 1 || j.ntaps > f64t::kMaxTaps || j.CH < 32 || rows < 48) return 2;
   const int chpad = round_up(j.CH, 16);
   if ((long long)chpad * 100 > j.CH * 115) return 2;                           // padded channels are wasted DMMAs
-  if (j.X[2] % 2 || ((uintptr_t)j.src & 15) || ((uintptr_t)j.wpack & 1023)) return 2;   // TMA strides are multiples of 16 B
-  for (int i = 0; i < 3; ++i) if (j.pmul[i] > 32 || j.P[i] < 1 || j.X[i] < 1) return 2;
-  if (j.pmul[2] != 1) return 2;          // the aligned 12-pixel box serves shifts of 0 / 1 pixel at stride 1 only
+  const int pitch2 = j.pitch2 ? j.pitch2 : j.X[2];
+  if (!dry && (pitch2 % 2 || ((uintptr_t)j.src & 15) || ((uintptr_t)j.wpack & 1023))) return 2;   // TMA strides are multiples of 16 B
+  for (int i = 0; i < 3; ++i) if (j.pmul[i] > 8 || j.P[i] < 1 || j.X[i] < 1) return 2;   // TMA traversal strides are <= 8
+  if (j.pmul[2] > 2) return 2;           // rows are contiguous along the innermost axis: instantiated for strides 1 and 2
   const bool wide = rows > 64;                                                   // 128 x 128 tiles, else 256 x 64
   const int BMt = wide ? 128 : 256;
   // pixel box: 8 along the last axis, BM / 8 over the other axes and the batch (powers of two), fewest tiles
@@ -1451,7 +1475,8 @@ int f64_fwdlike_tma(const F64Job& j, cudaStream_t st) {
       if (best < 0 || tiles < best) { best = tiles; box[0] = b0; box[1] = b1; boxn = bn; }
     }
   const long long pixels = j.nbatch * j.P[0] * j.P[1] * j.P[2];
-  if (best < 0 || best > INT32_MAX || best * BMt * 100 > pixels * 118) return 2;   // ragged tiles would cost more than they save
+  if (best < 0 || best > INT32_MAX || best * BMt * 100 > pixels * 130) return 2;   // ragged tiles would cost more than they save
+  if (dry) return 0;
   f64t::FwdLikeParams fp;
   fp.out = j.out; fp.om = j.om;
   for (int i = 0; i < 3; ++i) {
@@ -1473,11 +1498,11 @@ int f64_fwdlike_tma(const F64Job& j, cudaStream_t st) {
   MGB_LAUNCH_CHECK();
   CUtensorMap ma, mb;
   {
-    const cuuint64_t xp = (cuuint64_t)j.X[0] * j.X[1] * j.X[2];
+    const cuuint64_t xp = (cuuint64_t)j.X[0] * j.X[1] * pitch2;
     cuuint64_t dims[5] = {(cuuint64_t)j.X[2], (cuuint64_t)j.CH, (cuuint64_t)j.X[1], (cuuint64_t)j.X[0], (cuuint64_t)j.nbatch};
-    cuuint64_t strides[4] = {xp * 8, (cuuint64_t)j.X[2] * 8, (cuuint64_t)j.X[1] * j.X[2] * 8, (cuuint64_t)j.CH * xp * 8};
-    cuuint32_t bx[5] = {(cuuint32_t)f64t::AW, 16, (cuuint32_t)(box[1] * j.pmul[1]), (cuuint32_t)(box[0] * j.pmul[0]),
-                        (cuuint32_t)boxn};
+    cuuint64_t strides[4] = {xp * 8, (cuuint64_t)pitch2 * 8, (cuuint64_t)j.X[1] * pitch2 * 8, (cuuint64_t)j.CH * xp * 8};
+    cuuint32_t bx[5] = {(cuuint32_t)f64t::row_pixels(j.pmul[2]), 16, (cuuint32_t)(box[1] * j.pmul[1]),
+                        (cuuint32_t)(box[0] * j.pmul[0]), (cuuint32_t)boxn};
     cuuint32_t estr[5] = {1, 1, (cuuint32_t)j.pmul[1], (cuuint32_t)j.pmul[0], 1};
     if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)j.src, dims, strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -1492,19 +1517,17 @@ int f64_fwdlike_tma(const F64Job& j, cudaStream_t st) {
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return 2;
   }
-  if (wide) {
-    constexpr int ST = 5;
-    auto kern = f64t::f64_fwdlike_tma_kernel<128, 128, ST>;
-    const size_t smem = f64t::fwdlike_smem_bytes<128, 128, ST>();
+  auto launch = [&](auto kern, size_t smem, int bn) -> int {
     MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)best, (unsigned)((rows + 127) / 128)), f64t::THREADS, smem, st>>>(fp, ma, mb);
-  } else {
-    constexpr int ST = 4;
-    auto kern = f64t::f64_fwdlike_tma_kernel<256, 64, ST>;
-    const size_t smem = f64t::fwdlike_smem_bytes<256, 64, ST>();
-    MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)best, (unsigned)((rows + 63) / 64)), f64t::THREADS, smem, st>>>(fp, ma, mb);
-  }
+    kern<<<dim3((unsigned)best, (unsigned)((rows + bn - 1) / bn)), f64t::THREADS, smem, st>>>(fp, ma, mb);
+    return 0;
+  };
+  int lrc;
+  if (wide && j.pmul[2] == 1) lrc = launch(f64t::f64_fwdlike_tma_kernel<128, 128, 5, 1>, f64t::fwdlike_smem_bytes<128, 128, 5, 1>(), 128);
+  else if (wide)              lrc = launch(f64t::f64_fwdlike_tma_kernel<128, 128, 4, 2>, f64t::fwdlike_smem_bytes<128, 128, 4, 2>(), 128);
+  else if (j.pmul[2] == 1)    lrc = launch(f64t::f64_fwdlike_tma_kernel<256, 64, 4, 1>, f64t::fwdlike_smem_bytes<256, 64, 4, 1>(), 64);
+  else                        lrc = launch(f64t::f64_fwdlike_tma_kernel<256, 64, 2, 2>, f64t::fwdlike_smem_bytes<256, 64, 2, 2>(), 64);
+  if (lrc) return lrc;
   MGB_LAUNCH_CHECK();
   return 0;
 }
@@ -1536,7 +1559,16 @@ int fwd_t(const Plan& p, const T* x, const T* w, T* y, void* ws, size_t ws_bytes
       }
       j.w = w; j.F = p.F; j.C = p.C; j.Wp = p.Wp; j.rows_are_f = 1;
       j.out = y; j.om = fp.om; j.wpack = align1024((char*)ws + fwd_tab_bytes(p));
-      const int rc = f64_fwdlike_tma(j, st);
+      bool go = true;
+      if (p.X[2] & 1) {                      // odd rows: pitched copy first (only when the kernel will run)
+        go = f64_fwdlike_tma(j, st, true) == 0;
+        if (go) {
+          double* xp2 = align1024((char*)j.wpack + f64_pack_bytes(p.F, p.Wp, p.C));
+          if (f64_pitch_copy((const double*)x, xp2, p.N * p.C * p.X[0] * p.X[1], p.X[2], st)) return 1;
+          j.src = xp2; j.pitch2 = f64_pitch(p.X[2]);
+        }
+      }
+      const int rc = go ? f64_fwdlike_tma(j, st) : 2;
       if (rc != 2) return rc;
     }
   }
@@ -1558,8 +1590,11 @@ int dgrad_t(const Plan& p, const T* dy, const T* w, T* dx, void* ws, size_t ws_b
   std::vector<DgradClassPlan> cls;
   size_t need = 0;
   dgrad_classes(p, sizeof(T), &cls, &need);
+  const size_t need_classes = need;
+  if (sizeof(T) == 8) need += f64_pitched_bytes(p.N * p.F * p.G[0] * p.G[1], p.G[2]);
   if (ws_bytes < need || (need && !ws)) return fail("conv dgrad: workspace %zu < %zu bytes", ws_bytes, need);
   if (dgrad_needs_memset(p, cls)) MGB_CUDA(cudaMemsetAsync(dx, 0, (size_t)n_dx * sizeof(T), st));
+  const double* dy_pitched = nullptr;      // float64 with odd rows: made once, when the first class wants it
   for (auto& c : cls) {
     TapEntry* tab = (TapEntry*)((char*)ws + c.tab_off);
     T* wpack = (T*)((char*)ws + c.wp_off);
@@ -1589,7 +1624,17 @@ int dgrad_t(const Plan& p, const T* dy, const T* w, T* dx, void* ws, size_t ws_b
         }
         j.w = w; j.F = p.F; j.C = p.C; j.Wp = p.Wp; j.rows_are_f = 0;
         j.out = dx; j.om = fp.om; j.wpack = align1024(wpack);
-        const int rc = f64_fwdlike_tma(j, st);
+        bool go = true;
+        if (p.G[2] & 1) {
+          go = f64_fwdlike_tma(j, st, true) == 0;
+          if (go && !dy_pitched) {
+            double* d2 = align1024((char*)ws + need_classes);
+            if (f64_pitch_copy((const double*)dy, d2, p.N * p.F * p.G[0] * p.G[1], p.G[2], st)) return 1;
+            dy_pitched = d2;
+          }
+          if (go) { j.src = dy_pitched; j.pitch2 = f64_pitch(p.G[2]); }
+        }
+        const int rc = go ? f64_fwdlike_tma(j, st) : 2;
         if (rc == 1) return 1;
         if (rc == 0) continue;
       }
@@ -1611,20 +1656,29 @@ struct F64WgradPlan {
 
 // geometry-only part of the decision (also sizes the workspace): false = not applicable
 bool f64_wgrad_tma_plan(const Plan& p, F64WgradPlan* out) {
-  if (p.dtype != MGB_F64 || p.F < 96 || p.C < 32 || p.S[2] != 1 || p.G[2] % 2 || p.X[2] % 2) return false;
-  if (2 * p.S[1] > 256 || p.N * p.Gp == 0) return false;
+  if (p.dtype != MGB_F64 || p.F < 96 || p.C < 32) return false;
+  if (p.S[0] > 8 || p.S[1] > 8 || p.S[2] > 2 || p.N * p.Gp == 0) return false;   // TMA traversal strides <= 8; innermost: 1 or 2
   F64WgradPlan w;
   w.cblocks = (int)((p.C + 31) / 32);
   if ((long long)w.cblocks * 32 * 100 > p.C * 115) return false;               // padded channels are wasted DMMAs
   w.nblocks = (int)p.Wp * w.cblocks;
   const int pad3 = (w.nblocks + 2) / 3 * 3, pad4 = (w.nblocks + 3) / 4 * 4;
   w.NB = pad3 < pad4 ? 3 : 4;
-  if ((long long)std::min(pad3, pad4) * 100 > (long long)w.nblocks * 125) return false;
+  if ((long long)std::min(pad3, pad4) * 100 > (long long)w.nblocks * 134) return false;
   w.tiles1 = (p.G[1] + 1) / 2; w.tiles2 = (p.G[2] + 7) / 8;
   w.boxes = (long long)p.N * p.G[0] * w.tiles1 * w.tiles2;
-  if (w.boxes > INT32_MAX || w.boxes * 16 * 100 > p.N * p.Gp * 120) return false;   // ragged 2 x 8 boxes
+  if (w.boxes > INT32_MAX || w.boxes * 16 * 100 > p.N * p.Gp * 130) return false;   // ragged 2 x 8 boxes
   w.mt = (int)((p.F + 127) / 128); w.nt = (w.nblocks + w.NB - 1) / w.NB;
-  int splits = (int)std::max<long long>(1, std::min<long long>(std::max(1, sm_count() / (w.mt * w.nt)), w.boxes / 8));
+  // K splits: the split count whose CTA count fills whole waves of the machine best (one CTA per SM), with at
+  // least 32 k-slabs per split; ties go to fewer splits (less partial-sum traffic)
+  const int tiles = w.mt * w.nt, sms = sm_count();
+  int splits = 1;
+  double best_eff = 0.0;
+  for (int s2 = 1; s2 <= 64 && (s2 == 1 || w.boxes / s2 >= 32); ++s2) {
+    const long long ctas = (long long)tiles * s2;
+    const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+    if (eff > best_eff + 0.02) { best_eff = eff; splits = s2; }
+  }
   w.per = (w.boxes + splits - 1) / splits;
   w.splits = (int)((w.boxes + w.per - 1) / w.per);
   *out = w;
@@ -1632,15 +1686,30 @@ bool f64_wgrad_tma_plan(const Plan& p, F64WgradPlan* out) {
 }
 
 // returns 0 ok (sets *splits), 1 error, 2 not applicable
-int f64_wgrad_tma(const Plan& p, const double* dy, const double* x, double* partial, int* splits, cudaStream_t st) {
+// `pitched`: workspace for the even-pitch copies of dy and x when their rows are odd (f64_pitched_bytes each)
+int f64_wgrad_tma(const Plan& p, const double* dy, const double* x, double* partial, void* pitched, int* splits,
+                  cudaStream_t st) {
   EncodeTiledFn enc = tma_encoder();
   F64WgradPlan w;
   if (!enc || !f64_tma_enabled() || !f64_wgrad_tma_plan(p, &w)) return 2;
   if (((uintptr_t)dy & 15) || ((uintptr_t)x & 15)) return 2;
+  const int gp2 = f64_pitch(p.G[2]), xp2 = f64_pitch(p.X[2]);
+  if (p.G[2] & 1) {
+    double* d2 = align1024(pitched);
+    if (f64_pitch_copy(dy, d2, p.N * p.F * p.G[0] * p.G[1], p.G[2], st)) return 1;
+    dy = d2;
+    pitched = (char*)d2 + f64_pitched_bytes(p.N * p.F * p.G[0] * p.G[1], p.G[2]) - 1024;
+  }
+  if (p.X[2] & 1) {
+    double* x2 = align1024(pitched);
+    if (f64_pitch_copy(x, x2, p.N * p.C * p.X[0] * p.X[1], p.X[2], st)) return 1;
+    x = x2;
+  }
   CUtensorMap mdy, mx;
   {
     cuuint64_t dims[5] = {(cuuint64_t)p.G[2], (cuuint64_t)p.G[1], (cuuint64_t)p.G[0], (cuuint64_t)p.F, (cuuint64_t)p.N};
-    cuuint64_t strides[4] = {(cuuint64_t)p.G[2] * 8, (cuuint64_t)p.G[1] * p.G[2] * 8, (cuuint64_t)p.Gp * 8, (cuuint64_t)p.F * p.Gp * 8};
+    const cuuint64_t gpp = (cuuint64_t)p.G[0] * p.G[1] * gp2;
+    cuuint64_t strides[4] = {(cuuint64_t)gp2 * 8, (cuuint64_t)p.G[1] * gp2 * 8, gpp * 8, (cuuint64_t)p.F * gpp * 8};
     cuuint32_t bx[5] = {8, 2, 1, 128, 1}, estr[5] = {1, 1, 1, 1, 1};
     if (enc(&mdy, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)dy, dims, strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -1648,8 +1717,10 @@ int f64_wgrad_tma(const Plan& p, const double* dy, const double* x, double* part
   }
   {
     cuuint64_t dims[5] = {(cuuint64_t)p.X[2], (cuuint64_t)p.X[1], (cuuint64_t)p.X[0], (cuuint64_t)p.C, (cuuint64_t)p.N};
-    cuuint64_t strides[4] = {(cuuint64_t)p.X[2] * 8, (cuuint64_t)p.X[1] * p.X[2] * 8, (cuuint64_t)p.Xp * 8, (cuuint64_t)p.C * p.Xp * 8};
-    cuuint32_t bx[5] = {(cuuint32_t)f64t::WX, (cuuint32_t)(2 * p.S[1]), 1, 32, 1}, estr[5] = {1, (cuuint32_t)p.S[1], 1, 1, 1};
+    const cuuint64_t xpp = (cuuint64_t)p.X[0] * p.X[1] * xp2;
+    cuuint64_t strides[4] = {(cuuint64_t)xp2 * 8, (cuuint64_t)p.X[1] * xp2 * 8, xpp * 8, (cuuint64_t)p.C * xpp * 8};
+    cuuint32_t bx[5] = {(cuuint32_t)f64t::wg_row_pixels(p.S[2]), (cuuint32_t)(2 * p.S[1]), 1, 32, 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)p.S[1], 1, 1, 1};
     if (enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)x, dims, strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return 2;
@@ -1660,19 +1731,18 @@ int f64_wgrad_tma(const Plan& p, const double* dy, const double* x, double* part
   wp.F = (int)p.F; wp.C = (int)p.C; wp.Wp = (int)p.Wp; wp.cblocks = w.cblocks; wp.nblocks_total = w.nblocks;
   wp.tiles1 = w.tiles1; wp.tiles2 = w.tiles2;
   wp.boxes_total = (int)w.boxes; wp.boxes_per_split = (int)w.per;
-  constexpr int ST = 4;
   const dim3 grid(w.mt, w.nt, w.splits);
-  if (w.NB == 3) {
-    auto kern = f64t::f64_wgrad_tma_kernel<3, ST>;
-    const size_t smem = f64t::wgrad_smem_bytes<3, ST>();
+  auto launch = [&](auto kern, size_t smem) -> int {
     MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, f64t::THREADS, smem, st>>>(wp, mdy, mx);
-  } else {
-    auto kern = f64t::f64_wgrad_tma_kernel<4, ST>;
-    const size_t smem = f64t::wgrad_smem_bytes<4, ST>();
-    MGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, f64t::THREADS, smem, st>>>(wp, mdy, mx);
-  }
+    return 0;
+  };
+  int lrc;
+  if (w.NB == 3 && p.S[2] == 1)      lrc = launch(f64t::f64_wgrad_tma_kernel<3, 4, 1>, f64t::wgrad_smem_bytes<3, 4, 1>());
+  else if (w.NB == 3)                lrc = launch(f64t::f64_wgrad_tma_kernel<3, 3, 2>, f64t::wgrad_smem_bytes<3, 3, 2>());
+  else if (p.S[2] == 1)              lrc = launch(f64t::f64_wgrad_tma_kernel<4, 4, 1>, f64t::wgrad_smem_bytes<4, 4, 1>());
+  else                               lrc = launch(f64t::f64_wgrad_tma_kernel<4, 3, 2>, f64t::wgrad_smem_bytes<4, 3, 2>());
+  if (lrc) return lrc;
   MGB_LAUNCH_CHECK();
   *splits = w.splits;
   return 0;
@@ -1687,7 +1757,9 @@ size_t wgrad_ws(const Plan& p, int* splits, int* kps) {
   int slabs = *splits;
   F64WgradPlan w;
   if (sizeof(T) == 8 && f64_wgrad_tma_plan(p, &w)) slabs = std::max(slabs, w.splits);
-  off += (size_t)slabs * M * N * sizeof(T);
+  off += align_up((size_t)slabs * M * N * sizeof(T), 1024);
+  if (sizeof(T) == 8)      // even-pitch copies of dy / x for the TMA kernel
+    off += f64_pitched_bytes(p.N * p.F * p.G[0] * p.G[1], p.G[2]) + f64_pitched_bytes(p.N * p.C * p.X[0] * p.X[1], p.X[2]);
   return off;
 }
 
@@ -1708,7 +1780,9 @@ int wgrad_t(const Plan& p, const T* dy, const T* x, T* dw, void* ws, size_t ws_b
   T* partial = (T*)((char*)tabB + align_up((size_t)N * sizeof(TapEntry), 256));
   if constexpr (sizeof(T) == 8) {        // TMA-staged DMMA kernel first
     int s2 = 0;
-    const int rc = f64_wgrad_tma(p, dy, x, partial, &s2, st);
+    const size_t pitched_bytes = f64_pitched_bytes(p.N * p.F * p.G[0] * p.G[1], p.G[2]) +
+                                 f64_pitched_bytes(p.N * p.C * p.X[0] * p.X[1], p.X[2]);
+    const int rc = f64_wgrad_tma(p, dy, x, partial, (char*)ws + need - pitched_bytes, &s2, st);
     if (rc == 1) return 1;
     if (rc == 0) return finish_dw<T>(partial, dw, (long long)M * N, s2, st);
   }
@@ -1750,6 +1824,7 @@ extern "C" int mgb_conv_workspace_bytes(const mgb_conv_desc* d, int which, size_
   } else if (which == 1) {
     std::vector<DgradClassPlan> cls;
     dgrad_classes(p, esz, &cls, &need);
+    if (p.dtype == MGB_F64) need += f64_pitched_bytes(p.N * p.F * p.G[0] * p.G[1], p.G[2]);
     if (tc_eligible(p, 1)) need = tc_dgrad_ws(p, cls);
   } else if (which == 2) {
     int s, k;

@@ -27,7 +27,10 @@ namespace conv {
 namespace f64t {
 
 constexpr int BK = 16;
-constexpr int AW = 12;                       // pixels per row of the pixel operand in shared memory (8 used)
+// pixels per row of the pixel operand in shared memory for a gather stride PM along the innermost axis: TMA
+// cannot stride dimension 0 (elementStrides[0] is ignored), so the row is contiguous — 8 pixels PM apart,
+// + 1 for an odd start, rounded up so that 4 k-rows of 8 lanes spread over the banks (12 at PM = 1)
+constexpr int row_pixels(int pm) { return 8 * pm + 4; }
 constexpr int kMaxTaps = 128;
 constexpr int CONSUMERS = 8;
 // two MMA warpgroups + one producer warpgroup (only one thread of it works): register budgets move between
@@ -46,7 +49,7 @@ struct FwdLikeParams {
   double* out;
   OutMap om;
   int P[3];                    // pixel grid per sample
-  int pmul[3], base[3];        // source coord = pixel * pmul + base + tap delta; pmul[2] == 1
+  int pmul[3], base[3];        // source coord = pixel * pmul + base + tap delta (pmul[2] == the kernel's PM)
   int box[3], boxn;            // pixel box of one M tile: box[2] == 8, product == BM
   int tiles[3], tiles_n;
   int Nbatch, Nout;
@@ -54,9 +57,9 @@ struct FwdLikeParams {
   Taps taps;
 };
 
-template <int BM, int BN, int STAGES>
+template <int BM, int BN, int STAGES, int PM>
 constexpr size_t fwdlike_smem_bytes() {
-  return (size_t)STAGES * (BM / 8 * BK * AW * 8 + BN * BK * 8) + 1024 + 256;
+  return (size_t)STAGES * (BM / 8 * BK * row_pixels(PM) * 8 + BN * BK * 8) + 1024 + 256;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -71,13 +74,14 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 
 // D[pixel, channel] = sum_{tap, c} T[pixel * pmul + base + delta(tap), c] * B[channel][tap][c]
 // grid = (M tiles, ceil(Nout / BN)); 8 MMA warps of 64 x 32 + a producer warpgroup
-template <int BM, int BN, int STAGES>
+template <int BM, int BN, int STAGES, int PM>
 __global__ void __launch_bounds__(THREADS, 1)
 f64_fwdlike_tma_kernel(const __grid_constant__ FwdLikeParams p, const __grid_constant__ CUtensorMap map_a,
                        const __grid_constant__ CUtensorMap map_b) {
   static_assert((BM / 64) * (BN / 32) == CONSUMERS, "8 MMA warps of 64 x 32");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int AW = row_pixels(PM);
   constexpr int A_STAGE = BM / 8 * BK * AW * 8, B_STAGE = BN * BK * 8;
   static_assert((STAGES * A_STAGE) % 1024 == 0, "the swizzled B ring starts 1024-byte aligned");
   uint8_t* a_ring = smem;
@@ -109,7 +113,7 @@ f64_fwdlike_tma_kernel(const __grid_constant__ FwdLikeParams p, const __grid_con
     reg_dealloc<40>();
     if (warp == CONSUMERS && tc::elect_one()) {
       // ===== producer =====
-      const int x0 = g0 * p.pmul[0] + p.base[0], x1 = g1 * p.pmul[1] + p.base[1], x2 = g2 + p.base[2];
+      const int x0 = g0 * p.pmul[0] + p.base[0], x1 = g1 * p.pmul[1] + p.base[1], x2 = g2 * PM + p.base[2];
       int tap = 0, cc = 0;
       for (int s = 0; s < S; ++s) {
         const int stage = s % STAGES;
@@ -135,7 +139,7 @@ f64_fwdlike_tma_kernel(const __grid_constant__ FwdLikeParams p, const __grid_con
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // fragment offsets that do not depend on the stage
-  const int a_off = ((warp_m >> 3) * BK + lk) * AW + lr;                // doubles: [group][k][AW]
+  const int a_off = ((warp_m >> 3) * BK + lk) * AW + lr * PM;           // doubles: [group][k][AW]
   int b_off[4];                                                        // bytes, chunk swizzle applied per kk
 #pragma unroll
   for (int j = 0; j < 4; ++j) b_off[j] = (warp_n + j * 8 + lr) * 128 + (lk & 1) * 8;
@@ -197,14 +201,14 @@ f64_fwdlike_tma_kernel(const __grid_constant__ FwdLikeParams p, const __grid_con
 // its own 128-byte line (measured: scripts/probes/tma_f64_probe.cu variant 9), so the slab occupies 32 KB
 // for 16 KB of data and line (2 f + row) holds chunk c at 16-byte slot c ^ (line & 7): 8 filters x 4 k of an
 // A fragment land on all banks exactly twice — and, for each of the
-// N tile's (tap, 32-channel) blocks, x as [32 channels][2 rows][WX pixels]: WX = 10 because the tap shifts
-// the start by single pixels and TMA wants it even (see above); 160-byte rows put the 8 columns x 4 k of
-// a B fragment on all banks exactly twice.  Conv strides along the outer axes are the map's traversal
-// strides; the innermost axis must have stride 1.
-constexpr int WX = 10;
+// N tile's (tap, 32-channel) blocks, x as [32 channels][2 rows][WX pixels]: contiguous rows of 8 S2 + 2 pixels
+// (the tap shifts the start by single pixels and TMA wants it even, see above; TMA cannot stride dimension 0);
+// at S2 = 1 the 160-byte rows put the 8 columns x 4 k of a B fragment on all banks exactly twice.  Conv
+// strides along the outer axes are the map's traversal strides.
+constexpr int wg_row_pixels(int s2) { return 8 * s2 + 2; }
 constexpr int WG_A_BYTES = 128 * BK * 8;             // dy slab: bytes TMA delivers
 constexpr int WG_A_STAGE = 2 * WG_A_BYTES;           // ... and its footprint (64-byte rows in 128-byte lines)
-constexpr int WG_BLK = 32 * 2 * WX * 8;              // one (tap, 32-channel) block of x
+constexpr int wg_blk_bytes(int s2) { return 32 * 2 * wg_row_pixels(s2) * 8; }   // one (tap, 32-channel) block of x
 
 struct WgradParams {
   double* partial;             // [splits][F][C][Wp]
@@ -215,17 +219,18 @@ struct WgradParams {
   int boxes_total, boxes_per_split;
 };
 
-template <int NB, int STAGES>
+template <int NB, int STAGES, int S2>
 constexpr size_t wgrad_smem_bytes() {
-  return (size_t)STAGES * (WG_A_STAGE + NB * WG_BLK) + 1024 + 256;
+  return (size_t)STAGES * (WG_A_STAGE + NB * wg_blk_bytes(S2)) + 1024 + 256;
 }
 
 // grid = (ceil(F / 128), ceil(nblocks / NB), splits); NB = 3 or 4 blocks of 32 columns per N tile
-template <int NB, int STAGES>
+template <int NB, int STAGES, int S2>
 __global__ void __launch_bounds__(THREADS, 1)
 f64_wgrad_tma_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ CUtensorMap map_dy,
                      const __grid_constant__ CUtensorMap map_x) {
   constexpr int BN = NB * 32, WN = BN / 4, NI = WN / 8;          // 8 MMA warps: 2 (M) x 4 (N), 64 x WN each
+  constexpr int WX = wg_row_pixels(S2), WG_BLK = wg_blk_bytes(S2);
   constexpr int STAGE = WG_A_STAGE + NB * WG_BLK;
   static_assert(STAGE % 1024 == 0, "swizzled dy slabs start 1024-byte aligned");
   extern __shared__ uint8_t smem_raw[];
@@ -283,7 +288,7 @@ f64_wgrad_tma_kernel(const __grid_constant__ WgradParams p, const __grid_constan
 #pragma unroll
         for (int b = 0; b < NB; ++b)
           if (b < nvalid)
-            tma::tma_load_5d(a_dst + WG_A_STAGE + b * WG_BLK, &map_x, full_bar + stage, (g2 * p.S[2] + bd2[b]) & ~1,
+            tma::tma_load_5d(a_dst + WG_A_STAGE + b * WG_BLK, &map_x, full_bar + stage, (g2 * S2 + bd2[b]) & ~1,
                              g1 * p.S[1] + bd1[b], g0 * p.S[0] + bd0[b], bcb[b] * 32, n);
       }
     }
@@ -309,7 +314,7 @@ f64_wgrad_tma_kernel(const __grid_constant__ WgradParams p, const __grid_constan
     const int col = warp_n + j * 8;
     int d0, d1, d2, cb;
     tap_delta(min(blk0 + col / 32, p.nblocks_total - 1), d0, d1, d2, cb);
-    b_off[j] = WG_A_STAGE + (col + lr) * (2 * WX * 8) + ((d2 & 1) + lk) * 8;      // g2 * S2 is even (S2 == 1, g2 % 8 == 0)
+    b_off[j] = WG_A_STAGE + (col + lr) * (2 * WX * 8) + ((d2 & 1) + lk * S2) * 8;      // g2 * S2 is even (g2 % 8 == 0)
   }
 
   for (int s = 0; s < S; ++s) {
@@ -323,7 +328,7 @@ f64_wgrad_tma_kernel(const __grid_constant__ WgradParams p, const __grid_constan
       const int chunk = row * 128 + (((2 * (kk & 1) + (lk >> 1)) ^ ((lr & 3) * 2 + row)) << 4);
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const double*>(st + a_off[i] + chunk);
-      const int koff = (row * WX + (kk & 1) * 4) * 8;
+      const int koff = (row * WX + (kk & 1) * 4 * S2) * 8;
 #pragma unroll
       for (int j = 0; j < NI; ++j) b[j] = *reinterpret_cast<const double*>(st + b_off[j] + koff);
 #pragma unroll

@@ -262,6 +262,8 @@ F64_CASES = [
     (1, 32, 96, (5, 8, 12), (2, 3, 3), (1, 1, 1), (0, 1, 1), 1),   # 3-D
     (2, 64, 128, (15, 15), (3, 3), 1, 1, 1),            # odd row length: byte strides not multiples of 16, no TMA at all
     (2, 64, 128, (40,), (5,), 1, 2, 1),                 # 1-D
+    (2, 64, 128, (17, 18), (3, 2), 2, (1, 0), 1),       # stride 2 on the innermost axis: contiguous rows read 2 apart
+    (4, 32, 96, (37, 37), (5, 5), 2, 0, 2),             # config 3 in small: stride 2, dilation 2, odd rows of x and dy
 ]
 
 
