@@ -520,7 +520,7 @@ class Harness:
             achieved = ph["gbs"]
             roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_basis": src}
-        for tf in ("r02_traffic.json", "r01_traffic.json"):     # DRAM bytes of that kernel from the committed ncu capture
+        for tf in ("r02b_traffic.json", "r02_traffic.json", "r01_traffic.json"):     # DRAM bytes of that kernel from the committed ncu capture
             tfile = ROOT / "profiles" / tf
             if tfile.exists():
                 t = json.loads(tfile.read_text()).get(workload, {}).get(top)
