@@ -1255,6 +1255,12 @@ int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, const vo
     for (int k = 0; k < p.W[i]; ++k) { tb.kidx[i][k] = (short)k; tb.delta[i][k] = (short)(k * p.D[i]); }
   }
   tb.cpad = L.X.cpad;
+  // the row-halo kernel addresses taps by box coordinates: no tap table
+  {
+    const int rc = wgrad_rows_launch(p, L, xhi, xlo, yhi, ylo, partial, st);
+    if (rc == 1) return 1;
+    if (rc == 0) return finish_dw<float>(partial, dw, n_dw, L.tma_splits, st);
+  }
   build_tc_taps<<<1, 256, 0, st>>>(taps, list, tb);
   MGB_LAUNCH_CHECK();
   tc::TcWgradParams wp;
@@ -1264,10 +1270,9 @@ int tc_wgrad(const Plan& p, const float* dy, const float* x, float* dw, const vo
   for (int i = 0; i < 3; ++i) { wp.G[i] = p.G[i]; wp.S[i] = p.S[i]; wp.Pd[i] = p.Pd[i]; wp.X[i] = p.X[i]; }
   wp.gp = (int)p.Gp; wp.Ktot = (int)(p.N * p.Gp); wp.k_per_split = L.kps;
   wp.nblocks_total = L.nblocks; wp.nbpc = L.nbpc; wp.tmem_cols = pow2_cols(L.nbpc * 32);
-  // row-halo variant, then the per-tap TMA variant; the cp.async kernel is the fallback
+  // the per-tap TMA variant; the cp.async kernel is the fallback
   {
-    int rc = wgrad_rows_launch(p, L, xhi, xlo, yhi, ylo, partial, st);
-    if (rc == 2) rc = wgrad_tma_launch(p, L, xhi, xlo, yhi, ylo, taps, partial, st);
+    int rc = wgrad_tma_launch(p, L, xhi, xlo, yhi, ylo, taps, partial, st);
     if (rc == 1) return 1;
     if (rc == 0) {
       return finish_dw<float>(partial, dw, n_dw, L.tma_splits, st);
