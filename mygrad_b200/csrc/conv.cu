@@ -13,6 +13,7 @@
 #include "conv_halo2.cuh"
 #include "conv_wgrad2.cuh"
 #include "conv_f64_tma.cuh"
+#include "conv_thin.cuh"
 
 namespace mgb {
 namespace conv {
@@ -198,9 +199,96 @@ int launch_fwdlike(const FwdParams<T>& p, cudaStream_t st) {
   return 0;
 }
 
+// thin GEMMs (conv_thin.cuh): few taps x channels (K <= 64: a first layer) or very few output channels (dX of one).
+// MGB_CONV_THIN=0 keeps them on the MMA tiles.
+inline bool thin_enabled() {
+  const char* e = getenv("MGB_CONV_THIN");
+  return !(e && e[0] == '0');
+}
+
+template <typename T>
+bool thin_fwdlike_applies(const FwdParams<T>& p, int* nb, int* kp, size_t* smem) {
+  if (!thin_enabled() || !(p.K <= 64 || (p.N <= 8 && p.K <= 1024))) return false;
+  *nb = p.N <= 4 ? 4 : p.N <= 16 ? 16 : 32;
+  *kp = (p.K + 3) / 4 * 4;
+  *smem = (size_t)(*nb) * (*kp) * sizeof(T) + (size_t)p.K * sizeof(TapEntry);
+  return *smem <= 48 * 1024;
+}
+
+template <typename T, int NB, int PX>
+int launch_thin_fwdlike(const FwdParams<T>& p, int kp, size_t smem, cudaStream_t st) {
+  const long long groups = ((long long)p.M + thin::THREADS * PX - 1) / (thin::THREADS * PX);
+  dim3 grid((unsigned)groups, (unsigned)((p.N + NB - 1) / NB));
+  thin::thin_fwdlike_kernel<T, NB, PX><<<grid, thin::THREADS, smem, st>>>(p, kp);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- 1-D / 2-D thin layers with the input band staged in shared memory (conv_thin.cuh) ----
+struct Thin2dPlan { int R, nbands, RB, CB, CBp; size_t band_bytes; };
+
+bool thin2d_plan(const Plan& p, size_t esz, size_t max_band_bytes, Thin2dPlan* out) {
+  if (!thin_enabled() || p.X[0] != 1 || p.W[0] != 1 || p.G[0] != 1 || p.C * p.Wp > 64) return false;
+  if (p.N * p.Gp == 0 || p.N > INT32_MAX / 4) return false;
+  Thin2dPlan t;
+  t.CB = (p.G[2] - 1) * p.S[2] + (p.W[2] - 1) * p.D[2] + 1;
+  t.CBp = t.CB | 1;                                    // odd row stride: strided pixel columns spread over the banks
+  int R = std::min(p.G[1], std::max(1, 1024 / p.G[2]));
+  for (;; R /= 2) {
+    t.RB = (R - 1) * p.S[1] + (p.W[1] - 1) * p.D[1] + 1;
+    t.band_bytes = (size_t)p.C * t.RB * t.CBp * esz;
+    if (t.band_bytes <= max_band_bytes) break;
+    if (R == 1) return false;
+  }
+  t.R = R;
+  t.nbands = (p.G[1] + R - 1) / R;
+  if ((long long)p.N * t.nbands > INT32_MAX) return false;
+  *out = t;
+  return true;
+}
+
+template <typename T>
+thin::Thin2dParams<T> thin2d_params(const Plan& p, const Thin2dPlan& t) {
+  thin::Thin2dParams<T> q;
+  q.x = nullptr; q.w = nullptr; q.dy = nullptr; q.out = nullptr;
+  q.N = (int)p.N; q.C = (int)p.C; q.F = (int)p.F;
+  q.X1 = p.X[1]; q.X2 = p.X[2]; q.G1 = p.G[1]; q.G2 = p.G[2]; q.W1 = p.W[1]; q.W2 = p.W[2];
+  q.s1 = p.S[1]; q.s2 = p.S[2]; q.p1 = p.Pd[1]; q.p2 = p.Pd[2]; q.d1 = p.D[1]; q.d2 = p.D[2];
+  q.R = t.R; q.nbands = t.nbands; q.RB = t.RB; q.CB = t.CB; q.CBp = t.CBp;
+  return q;
+}
+
+// forward of a thin 1-D / 2-D layer: returns 0 ok, 1 error, 2 not applicable
+template <typename T>
+int thin2d_fwd(const Plan& p, const T* x, const T* w, T* y, cudaStream_t st) {
+  const int K = (int)(p.C * p.Wp), KP = (K + 3) / 4 * 4;
+  const int nb = (int)std::min<long long>(p.F, 64);   // filters per block (a run-time loop)
+  const size_t fixed = (size_t)nb * KP * sizeof(T) + (size_t)KP * sizeof(int);
+  Thin2dPlan t;
+  if (fixed > 16 * 1024 || !thin2d_plan(p, sizeof(T), 48 * 1024 - 16 * 1024, &t)) return 2;
+  thin::Thin2dParams<T> q = thin2d_params<T>(p, t);
+  q.x = x; q.w = w; q.out = y;
+  const size_t smem = fixed + t.band_bytes;
+  const int gy = (int)((p.F + nb - 1) / nb);
+  const int gx = (int)std::min<long long>(p.N * t.nbands, std::max(1, 6 * sm_count() / gy));
+  if (KP <= 32) thin::thin2d_fwd_kernel<T, 32, 2><<<dim3(gx, gy), thin::THREADS, smem, st>>>(q, KP, nb);
+  else thin::thin2d_fwd_kernel<T, 64, 1><<<dim3(gx, gy), thin::THREADS, smem, st>>>(q, KP, nb);
+  MGB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename T>
 int run_fwdlike(const FwdParams<T>& p, cudaStream_t st) {
   if (p.M == 0 || p.N == 0) return 0;
+  {
+    int nb, kp;
+    size_t smem;
+    if (thin_fwdlike_applies(p, &nb, &kp, &smem)) {
+      if (nb == 4) return launch_thin_fwdlike<T, 4, 4>(p, kp, smem, st);
+      if (nb == 16) return launch_thin_fwdlike<T, 16, 2>(p, kp, smem, st);
+      return launch_thin_fwdlike<T, 32, 2>(p, kp, smem, st);
+    }
+  }
   if (p.N > 64) return launch_fwdlike<T, typename Tiles<T>::Big>(p, st);
   if (p.N > 32) return launch_fwdlike<T, typename Tiles<T>::Mid>(p, st);
   return launch_fwdlike<T, typename Tiles<T>::Small>(p, st);
@@ -1577,6 +1665,10 @@ int fwd_t(const Plan& p, const T* x, const T* w, T* y, void* ws, size_t ws_bytes
       if (rc != 2) return rc;
     }
   }
+  {
+    const int rc = thin2d_fwd<T>(p, x, w, y, st);      // thin 1-D / 2-D layers: input band in shared memory
+    if (rc != 2) return rc;
+  }
   TapEntry* tab = (TapEntry*)ws;
   build_x_table<<<small_grid(K), 256, 0, st>>>(tab, x_table_args(p));
   MGB_LAUNCH_CHECK();
@@ -1753,10 +1845,32 @@ int f64_wgrad_tma(const Plan& p, const double* dy, const double* x, double* part
   return 0;
 }
 
+// thin wgrad (conv_thin.cuh): C * taps <= 64.  Plan: KB taps per warp, KG x FG warps per block, slabs of pixels.
+struct ThinWgradPlan { int KB, KG, FG, fgroups, splits; long long per; };
+template <typename T>
+bool thin_wgrad_plan(int M, int N, int K, ThinWgradPlan* out) {
+  if (!thin_enabled() || N > 64 || M < 1 || K < 1) return false;
+  ThinWgradPlan w;
+  w.KB = sizeof(T) == 4 ? 16 : 8;
+  w.KG = (N + w.KB - 1) / w.KB;                       // <= 4 (float) / 8 (double)
+  w.FG = std::max(1, std::min((M + 7) / 8, 8 / w.KG));
+  w.fgroups = (M + 8 * w.FG - 1) / (8 * w.FG);
+  long long want = std::max<long long>(1, (2LL * sm_count()) / w.fgroups);
+  w.splits = (int)std::max<long long>(1, std::min<long long>(want, ((long long)K + 1023) / 1024));
+  w.per = (((long long)K + w.splits - 1) / w.splits + 31) / 32 * 32;
+  w.splits = (int)(((long long)K + w.per - 1) / w.per);
+  *out = w;
+  return true;
+}
+
 template <typename T>
 size_t wgrad_ws(const Plan& p, int* splits, int* kps) {
   int M = (int)p.F, N = (int)(p.C * p.Wp), K = (int)(p.N * p.Gp);
   wgrad_plan<T>(M, N, K, splits, kps);
+  {
+    ThinWgradPlan tw;
+    if (thin_wgrad_plan<T>(M, N, K, &tw)) *splits = std::max(*splits, tw.splits);   // sizes the partial slabs below
+  }
   size_t off = align_up((size_t)M * sizeof(TapEntry), 256);
   off += align_up((size_t)N * sizeof(TapEntry), 256);
   int slabs = *splits;
@@ -1791,6 +1905,19 @@ int wgrad_t(const Plan& p, const T* dy, const T* x, T* dw, void* ws, size_t ws_b
     if (rc == 1) return 1;
     if (rc == 0) return finish_dw<T>(partial, dw, (long long)M * N, s2, st);
   }
+  {
+    ThinWgradPlan tw;
+    Thin2dPlan t2;
+    if (thin_wgrad_plan<T>(M, N, K, &tw) && thin2d_plan(p, sizeof(T), 24 * 1024, &t2)) {
+      constexpr int KB = sizeof(T) == 4 ? 16 : 8;
+      thin::Thin2dParams<T> q = thin2d_params<T>(p, t2);
+      q.x = x; q.dy = dy; q.out = partial;
+      const int blocks = (int)std::min<long long>(p.N * t2.nbands, std::min(splits, std::max(1, sm_count() / tw.fgroups)));
+      thin::thin2d_wgrad_kernel<T, KB><<<dim3(blocks, tw.fgroups), tw.FG * tw.KG * 32, 2 * t2.band_bytes, st>>>(q, tw.FG, tw.KG);
+      MGB_LAUNCH_CHECK();
+      return finish_dw<T>(partial, dw, (long long)M * N, blocks, st);
+    }
+  }
   build_chan_table<<<small_grid(M), 256, 0, st>>>(tabA, M, p.Gp);
   MGB_LAUNCH_CHECK();
   build_x_table<<<small_grid(N), 256, 0, st>>>(tabB, x_table_args(p));
@@ -1800,6 +1927,16 @@ int wgrad_t(const Plan& p, const T* dy, const T* x, T* dw, void* ws, size_t ws_b
   wp.ga = geom_dy_by_output(p);
   wp.gb = geom_x_by_output(p);
   wp.M = M; wp.N = N; wp.K = K; wp.k_per_split = kps;
+  {
+    ThinWgradPlan tw;
+    if (thin_wgrad_plan<T>(M, N, K, &tw)) {
+      constexpr int KB = sizeof(T) == 4 ? 16 : 8;
+      const size_t smem = (size_t)N * sizeof(TapEntry);
+      thin::thin_wgrad_kernel<T, KB><<<dim3(tw.splits, tw.fgroups), tw.FG * tw.KG * 32, smem, st>>>(wp, tw.FG, tw.KG, tw.per);
+      MGB_LAUNCH_CHECK();
+      return finish_dw<T>(partial, dw, (long long)M * N, tw.splits, st);
+    }
+  }
   int rc;
   switch (wgrad_family(M, N)) {
     case 0: rc = launch_wgrad<T, typename Tiles<T>::WBig>(wp, splits, st); break;

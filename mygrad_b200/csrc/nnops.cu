@@ -349,37 +349,51 @@ namespace {
 
 constexpr int kSkinnyMaxM = 32;
 
-// C[n][j] = sum_d A[n][d] * B[d][j]: one warp per row, lanes stride d, B^T staged in smem by chunks
-template <typename T>
+// All three kernels are templated on MP = m rounded up to 4 / 8 / 16 / 32 (a run-time `j < m` inside a 32-wide
+// unrolled loop issues 32 predicated FMAs for m = 10) and accumulate runs of at most 64-128 products in the input
+// type before adding them to a float64 total: float32 inputs keep float32 FMA rate, the long sums stay exact to
+// ~1e-7 (the reference's sgemm accumulates in float32 throughout).
+
+// C[n][j] = sum_d A[n][d] * B[d][j]: one warp per row, lanes stride d, B^T staged in smem by chunks ([j][chunk]:
+// conflict-free for lanes that stride k)
+template <typename T, int MP>
 __global__ void __launch_bounds__(256) skinny_fwd_kernel(const T* __restrict__ A, const T* __restrict__ B,
                                                          T* __restrict__ Cout, long long n, int d, int m,
                                                          int CH) {
   extern __shared__ unsigned char smem_raw2[];
-  T* bs = reinterpret_cast<T*>(smem_raw2);          // [chunk][m]
+  T* bs = reinterpret_cast<T*>(smem_raw2);          // [MP][CH]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
-  double acc[kSkinnyMaxM];
+  double acc[MP];
 #pragma unroll
-  for (int j = 0; j < kSkinnyMaxM; ++j) acc[j] = 0.0;
+  for (int j = 0; j < MP; ++j) acc[j] = 0.0;
   for (int d0 = 0; d0 < d; d0 += CH) {
     const int len = min(CH, d - d0);
     __syncthreads();
-    for (int i = threadIdx.x; i < len * m; i += blockDim.x) bs[i] = B[(long long)d0 * m + i];
+    for (int i = threadIdx.x; i < len * m; i += blockDim.x) {
+      const int k = i / m, j = i - k * m;
+      bs[j * CH + k] = B[(long long)d0 * m + i];
+    }
+    if (m < MP)
+      for (int i = threadIdx.x; i < (MP - m) * len; i += blockDim.x) bs[(m + i / len) * CH + i % len] = (T)0;
     __syncthreads();
     if (row < n) {
       const T* a = A + row * d + d0;
-      for (int k = lane; k < len; k += 32) {
-        const double av = (double)a[k];
-        const T* b = bs + k * m;
+      T part[MP];
 #pragma unroll
-        for (int j = 0; j < kSkinnyMaxM; ++j)
-          if (j < m) acc[j] += av * (double)b[j];
+      for (int j = 0; j < MP; ++j) part[j] = (T)0;
+      for (int k = lane; k < len; k += 32) {            // <= CH / 32 <= 32 products per run
+        const T av = a[k];
+#pragma unroll
+        for (int j = 0; j < MP; ++j) part[j] += av * bs[j * CH + k];
       }
+#pragma unroll
+      for (int j = 0; j < MP; ++j) acc[j] += (double)part[j];
     }
   }
   if (row < n) {
 #pragma unroll
-    for (int j = 0; j < kSkinnyMaxM; ++j)
+    for (int j = 0; j < MP; ++j)
       if (j < m) {
         double v = acc[j];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -389,56 +403,66 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const T* __restrict__ A
 }
 
 // dA[n][k] = sum_j G[n][j] * B[k][j]: threads over k (coalesced writes), B row in registers
-template <typename T>
+template <typename T, int MP>
 __global__ void __launch_bounds__(256) skinny_da_kernel(const T* __restrict__ G, const T* __restrict__ B,
                                                         T* __restrict__ dA, long long n, int d, int m) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  T brow[kSkinnyMaxM];
+  T brow[MP];
 #pragma unroll
-  for (int j = 0; j < kSkinnyMaxM; ++j) brow[j] = (k < d && j < m) ? B[(long long)k * m + j] : (T)0;
-  __shared__ T gs[64 * kSkinnyMaxM];
+  for (int j = 0; j < MP; ++j) brow[j] = (k < d && j < m) ? B[(long long)k * m + j] : (T)0;
+  __shared__ T gs[64 * MP];
   const long long r0 = (long long)blockIdx.y * 64;
   const int rows = (int)min(64LL, n - r0);
-  for (int i = threadIdx.x; i < rows * m; i += blockDim.x) gs[i] = G[r0 * m + i];
+  for (int i = threadIdx.x; i < rows * MP; i += blockDim.x) {
+    const int r = i / MP, j = i - r * MP;
+    gs[i] = j < m ? G[(r0 + r) * m + j] : (T)0;
+  }
   __syncthreads();
   if (k >= d) return;
   for (int r = 0; r < rows; ++r) {
-    double acc = 0.0;
+    T acc = (T)0;
 #pragma unroll
-    for (int j = 0; j < kSkinnyMaxM; ++j)
-      if (j < m) acc += (double)gs[r * m + j] * (double)brow[j];
-    dA[(r0 + r) * d + k] = (T)acc;
+    for (int j = 0; j < MP; ++j) acc += gs[r * MP + j] * brow[j];
+    dA[(r0 + r) * d + k] = acc;
   }
 }
 
 // dB[k][j] = sum_n A[n][k] * G[n][j]: threads over k, split over n with float64 partials
-template <typename T>
+template <typename T, int MP>
 __global__ void __launch_bounds__(256) skinny_db_kernel(const T* __restrict__ A, const T* __restrict__ G,
                                                         double* __restrict__ partial, long long n, int d, int m,
                                                         long long rows_per_split) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(n, r0 + rows_per_split);
-  __shared__ T gs[64 * kSkinnyMaxM];
-  double acc[kSkinnyMaxM];
+  __shared__ T gs[64 * MP];
+  double acc[MP];
 #pragma unroll
-  for (int j = 0; j < kSkinnyMaxM; ++j) acc[j] = 0.0;
+  for (int j = 0; j < MP; ++j) acc[j] = 0.0;
   for (long long rb = r0; rb < r1; rb += 64) {
     const int rows = (int)min(64LL, r1 - rb);
     __syncthreads();
-    for (int i = threadIdx.x; i < rows * m; i += blockDim.x) gs[i] = G[rb * m + i];
+    for (int i = threadIdx.x; i < rows * MP; i += blockDim.x) {
+      const int r = i / MP, j = i - r * MP;
+      gs[i] = j < m ? G[(rb + r) * m + j] : (T)0;
+    }
     __syncthreads();
-    if (k < d)
-      for (int r = 0; r < rows; ++r) {
-        const double av = (double)A[(rb + r) * d + k];
+    if (k < d) {
+      T part[MP];
 #pragma unroll
-        for (int j = 0; j < kSkinnyMaxM; ++j)
-          if (j < m) acc[j] += av * (double)gs[r * m + j];
+      for (int j = 0; j < MP; ++j) part[j] = (T)0;
+      for (int r = 0; r < rows; ++r) {                  // <= 64 products per run
+        const T av = A[(rb + r) * d + k];
+#pragma unroll
+        for (int j = 0; j < MP; ++j) part[j] += av * gs[r * MP + j];
       }
+#pragma unroll
+      for (int j = 0; j < MP; ++j) acc[j] += (double)part[j];
+    }
   }
   if (k < d) {
     double* out = partial + ((long long)blockIdx.y * d + k) * m;
 #pragma unroll
-    for (int j = 0; j < kSkinnyMaxM; ++j)
+    for (int j = 0; j < MP; ++j)
       if (j < m) out[j] = acc[j];
   }
 }
@@ -454,16 +478,16 @@ __global__ void __launch_bounds__(256) skinny_db_finish(const double* __restrict
   }
 }
 
-template <typename T>
-int skinny_t(int which, long long n, int d, int m, const T* a, const T* b, T* out, cudaStream_t st) {
+template <typename T, int MP>
+int skinny_mp(int which, long long n, int d, int m, const T* a, const T* b, T* out, cudaStream_t st) {
   if (which == 0) {
-    int ch = std::max(32, std::min(1024, (int)(40960 / (m * sizeof(T))) / 32 * 32));   // <= 40 KB of smem
-    size_t smem = (size_t)ch * m * sizeof(T);
-    skinny_fwd_kernel<T><<<(unsigned)((n + 7) / 8), 256, smem, st>>>(a, b, out, n, d, m, ch);
+    int ch = std::max(32, std::min(1024, (int)(40960 / (MP * sizeof(T))) / 32 * 32));   // <= 40 KB of smem
+    size_t smem = (size_t)ch * MP * sizeof(T);
+    skinny_fwd_kernel<T, MP><<<(unsigned)((n + 7) / 8), 256, smem, st>>>(a, b, out, n, d, m, ch);
     MGB_LAUNCH_CHECK();
   } else if (which == 1) {
     dim3 grid((d + 255) / 256, (unsigned)((n + 63) / 64));
-    skinny_da_kernel<T><<<grid, 256, 0, st>>>(a, b, out, n, d, m);
+    skinny_da_kernel<T, MP><<<grid, 256, 0, st>>>(a, b, out, n, d, m);
     MGB_LAUNCH_CHECK();
   } else {
     int kb = (d + 255) / 256;
@@ -472,7 +496,7 @@ int skinny_t(int which, long long n, int d, int m, const T* a, const T* b, T* ou
     splits = (int)((n + per - 1) / per);
     double* partial = nullptr;
     MGB_CUDA(cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)splits * d * m, st));
-    skinny_db_kernel<T><<<dim3(kb, splits), 256, 0, st>>>(a, b, partial, n, d, m, per);
+    skinny_db_kernel<T, MP><<<dim3(kb, splits), 256, 0, st>>>(a, b, partial, n, d, m, per);
     MGB_LAUNCH_CHECK();
     long long total = (long long)d * m;
     skinny_db_finish<T><<<(unsigned)std::min<long long>((total + 255) / 256, 1024), 256, 0, st>>>(partial, out, total, splits);
@@ -480,6 +504,14 @@ int skinny_t(int which, long long n, int d, int m, const T* a, const T* b, T* ou
     MGB_CUDA(cudaFreeAsync(partial, st));
   }
   return 0;
+}
+
+template <typename T>
+int skinny_t(int which, long long n, int d, int m, const T* a, const T* b, T* out, cudaStream_t st) {
+  if (m <= 4) return skinny_mp<T, 4>(which, n, d, m, a, b, out, st);
+  if (m <= 8) return skinny_mp<T, 8>(which, n, d, m, a, b, out, st);
+  if (m <= 16) return skinny_mp<T, 16>(which, n, d, m, a, b, out, st);
+  return skinny_mp<T, 32>(which, n, d, m, a, b, out, st);
 }
 
 }  // namespace
