@@ -268,6 +268,26 @@ int thin2d_fwd(const Plan& p, const T* x, const T* w, T* y, cudaStream_t st) {
   if (fixed > 16 * 1024 || !thin2d_plan(p, sizeof(T), 48 * 1024 - 16 * 1024, &t)) return 2;
   thin::Thin2dParams<T> q = thin2d_params<T>(p, t);
   q.x = x; q.w = w; q.out = y;
+  if constexpr (sizeof(T) == 4) {          // float32: mma.sync 3xTF32 on fragments gathered from the band
+    const char* em = getenv("MGB_THIN_MMA");
+    if (!(em && em[0] == '0')) {
+      const int fb = (int)std::min<long long>(p.F, 64);
+      const int nt = fb <= 8 ? 1 : fb <= 16 ? 2 : fb <= 32 ? 4 : 8;
+      const int kp8 = (K + 7) / 8 * 8, np = nt * 8 + ((nt * 8) % 32 == 0 ? 8 : 0);
+      const size_t sm = (size_t)2 * kp8 * np * 4 + (size_t)kp8 * 4 + t.band_bytes;
+      if (sm <= 48 * 1024) {
+        const int gy2 = (int)((p.F + nt * 8 - 1) / (nt * 8));
+        const int gx2 = (int)std::min<long long>(p.N * t.nbands, std::max(1, 4 * sm_count() / gy2));
+        const dim3 grid(gx2, gy2);
+        if (nt == 1) thin::thin2d_fwd_mma_kernel<1, 2><<<grid, 256, sm, st>>>(q, kp8, np);
+        else if (nt == 2) thin::thin2d_fwd_mma_kernel<2, 2><<<grid, 256, sm, st>>>(q, kp8, np);
+        else if (nt == 4) thin::thin2d_fwd_mma_kernel<4, 2><<<grid, 256, sm, st>>>(q, kp8, np);
+        else thin::thin2d_fwd_mma_kernel<8, 2><<<grid, 256, sm, st>>>(q, kp8, np);
+        MGB_LAUNCH_CHECK();
+        return 0;
+      }
+    }
+  }
   const size_t smem = fixed + t.band_bytes;
   const int gy = (int)((p.F + nb - 1) / nb);
   const int gx = (int)std::min<long long>(p.N * t.nbands, std::max(1, 6 * sm_count() / gy));
@@ -1855,7 +1875,7 @@ bool thin_wgrad_plan(int M, int N, int K, ThinWgradPlan* out) {
   w.KG = (N + w.KB - 1) / w.KB;                       // <= 4 (float) / 8 (double)
   w.FG = std::max(1, std::min((M + 7) / 8, 8 / w.KG));
   w.fgroups = (M + 8 * w.FG - 1) / (8 * w.FG);
-  long long want = std::max<long long>(1, (2LL * sm_count()) / w.fgroups);
+  long long want = std::max<long long>(1, (3LL * sm_count()) / w.fgroups);
   w.splits = (int)std::max<long long>(1, std::min<long long>(want, ((long long)K + 1023) / 1024));
   w.per = (((long long)K + w.splits - 1) / w.splits + 31) / 32 * 32;
   w.splits = (int)(((long long)K + w.per - 1) / w.per);
@@ -1912,6 +1932,25 @@ int wgrad_t(const Plan& p, const T* dy, const T* x, T* dw, void* ws, size_t ws_b
       constexpr int KB = sizeof(T) == 4 ? 16 : 8;
       thin::Thin2dParams<T> q = thin2d_params<T>(p, t2);
       q.x = x; q.dy = dy; q.out = partial;
+      if constexpr (sizeof(T) == 4) {      // float32: mma.sync 3xTF32, one slab of partials per block
+        const char* em = getenv("MGB_THIN_MMA");
+        if (!(em && em[0] == '0')) {
+          const int fb = std::min(M, 64);
+          const int mt = fb <= 16 ? 1 : fb <= 32 ? 2 : 4, nt = N <= 32 ? 4 : 8;
+          const int gy = (M + mt * 16 - 1) / (mt * 16);
+          const int bx = (int)std::min<long long>(p.N * t2.nbands, std::min(splits, std::max(1, 3 * sm_count() / gy)));
+          const size_t sm = std::max<size_t>(2 * t2.band_bytes, (size_t)mt * 16 * nt * 8 * 4);
+          const dim3 grid(bx, gy);
+          if (mt == 1 && nt == 4) thin::thin2d_wgrad_mma_kernel<1, 4><<<grid, 256, sm, st>>>(q);
+          else if (mt == 2 && nt == 4) thin::thin2d_wgrad_mma_kernel<2, 4><<<grid, 256, sm, st>>>(q);
+          else if (mt == 4 && nt == 4) thin::thin2d_wgrad_mma_kernel<4, 4><<<grid, 256, sm, st>>>(q);
+          else if (mt == 1) thin::thin2d_wgrad_mma_kernel<1, 8><<<grid, 256, sm, st>>>(q);
+          else if (mt == 2) thin::thin2d_wgrad_mma_kernel<2, 8><<<grid, 256, sm, st>>>(q);
+          else thin::thin2d_wgrad_mma_kernel<4, 8><<<grid, 256, sm, st>>>(q);
+          MGB_LAUNCH_CHECK();
+          return finish_dw<T>(partial, dw, (long long)M * N, bx, st);
+        }
+      }
       const int blocks = (int)std::min<long long>(p.N * t2.nbands, std::min(splits, std::max(1, sm_count() / tw.fgroups)));
       thin::thin2d_wgrad_kernel<T, KB><<<dim3(blocks, tw.fgroups), tw.FG * tw.KG * 32, 2 * t2.band_bytes, st>>>(q, tw.FG, tw.KG);
       MGB_LAUNCH_CHECK();
