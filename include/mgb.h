@@ -254,6 +254,13 @@ int mgb_event_record(void* event, void* stream);
 int mgb_event_synchronize(void* event);
 int mgb_event_elapsed_ms(void* start, void* stop, float* ms);
 int mgb_stream_wait_event(void* stream, void* event);
+/* CUDA graphs for launch-bound steps: everything the calling thread enqueues on `stream` (not the legacy default
+ * stream) between begin and end is recorded instead of executed; mgb_graph_launch replays it.  The reference has no
+ * counterpart (it runs NumPy eagerly); mygrad_b200.StepGraph is the Python face. */
+int mgb_graph_begin(void* stream);
+int mgb_graph_end(void* stream, void** graph_exec, int* kernel_nodes);
+int mgb_graph_launch(void* graph_exec, void* stream);
+int mgb_graph_destroy(void* graph_exec);
 /* number of kernels this library has launched in this process (bench.py's
  * gpu_launches claim is read from here) */
 int mgb_launch_count(uint64_t* count);

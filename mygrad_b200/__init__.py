@@ -36,6 +36,7 @@ from .nnet.layers import conv_nd, conv_pool, max_pool, mean_pool
 from .math_ops import add, matmul, reshape
 from ._io import load, save
 from .linalg import einsum
+from .graph import StepGraph
 
 execute_op = Tensor._op  # same alias as mygrad.execute_op (src/mygrad/__init__.py:52)
 
@@ -46,6 +47,6 @@ __all__ = [
     "DeviceArray", "asdevice", "empty", "zeros", "full", "full_like", "pinned_empty",
     "current_stream", "set_stream", "synchronize", "device_available", "empty_cache",
     "InvalidGradient", "InvalidBackprop", "DisconnectedView", "SkipGradient",
-    "nnet", "conv_nd", "max_pool", "mean_pool", "conv_pool", "add", "matmul", "reshape", "einsum", "save", "load", "HostLayerPipeline",
+    "nnet", "conv_nd", "max_pool", "mean_pool", "conv_pool", "add", "matmul", "reshape", "einsum", "save", "load", "HostLayerPipeline", "StepGraph",
     "lib", "LIB_PATH",
 ]

@@ -115,6 +115,10 @@ EXPORTS = {
     "mgb_event_synchronize": (_i, [_vp]),
     "mgb_event_elapsed_ms": (_i, [_vp, _vp, C.POINTER(C.c_float)]),
     "mgb_stream_wait_event": (_i, [_vp, _vp]),
+    "mgb_graph_begin": (_i, [_vp]),
+    "mgb_graph_end": (_i, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "mgb_graph_launch": (_i, [_vp, _vp]),
+    "mgb_graph_destroy": (_i, [_vp]),
     "mgb_launch_count": (_i, [C.POINTER(C.c_uint64)]),
     "mgb_last_error": (C.c_char_p, []),
     "mgb_version": (C.c_char_p, []),

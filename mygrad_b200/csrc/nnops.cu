@@ -354,52 +354,60 @@ constexpr int kSkinnyMaxM = 32;
 // type before adding them to a float64 total: float32 inputs keep float32 FMA rate, the long sums stay exact to
 // ~1e-7 (the reference's sgemm accumulates in float32 throughout).
 
-// C[n][j] = sum_d A[n][d] * B[d][j]: one warp per row, lanes stride d, B^T staged in smem by chunks ([j][chunk]:
-// conflict-free for lanes that stride k)
+// C[n][j] = sum_d A[n][d] * B[d][j]: a warp owns RW rows, lanes stride d, B^T staged in smem by chunks
+// ([j][chunk + 1]: the odd stride keeps both the transposing store and the lane-strided reads conflict-free)
+constexpr int kSkinnyRows = 2;            // rows per warp: the staged chunk of B is used 16 times per block
 template <typename T, int MP>
 __global__ void __launch_bounds__(256) skinny_fwd_kernel(const T* __restrict__ A, const T* __restrict__ B,
                                                          T* __restrict__ Cout, long long n, int d, int m,
                                                          int CH) {
   extern __shared__ unsigned char smem_raw2[];
-  T* bs = reinterpret_cast<T*>(smem_raw2);          // [MP][CH]
+  T* bs = reinterpret_cast<T*>(smem_raw2);          // [MP][CH + 1]
+  const int CHP = CH + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + warp;
-  double acc[MP];
+  const long long row0 = ((long long)blockIdx.x * 8 + warp) * kSkinnyRows;
+  double acc[kSkinnyRows][MP];
 #pragma unroll
-  for (int j = 0; j < MP; ++j) acc[j] = 0.0;
+  for (int r = 0; r < kSkinnyRows; ++r)
+#pragma unroll
+    for (int j = 0; j < MP; ++j) acc[r][j] = 0.0;
   for (int d0 = 0; d0 < d; d0 += CH) {
     const int len = min(CH, d - d0);
     __syncthreads();
     for (int i = threadIdx.x; i < len * m; i += blockDim.x) {
       const int k = i / m, j = i - k * m;
-      bs[j * CH + k] = B[(long long)d0 * m + i];
+      bs[j * CHP + k] = B[(long long)d0 * m + i];
     }
     if (m < MP)
-      for (int i = threadIdx.x; i < (MP - m) * len; i += blockDim.x) bs[(m + i / len) * CH + i % len] = (T)0;
+      for (int i = threadIdx.x; i < (MP - m) * len; i += blockDim.x) bs[(m + i / len) * CHP + i % len] = (T)0;
     __syncthreads();
-    if (row < n) {
-      const T* a = A + row * d + d0;
+#pragma unroll
+    for (int r = 0; r < kSkinnyRows; ++r) {
+      if (row0 + r >= n) continue;
+      const T* a = A + (row0 + r) * d + d0;
       T part[MP];
 #pragma unroll
       for (int j = 0; j < MP; ++j) part[j] = (T)0;
       for (int k = lane; k < len; k += 32) {            // <= CH / 32 <= 32 products per run
         const T av = a[k];
 #pragma unroll
-        for (int j = 0; j < MP; ++j) part[j] += av * bs[j * CH + k];
+        for (int j = 0; j < MP; ++j) part[j] += av * bs[j * CHP + k];
       }
 #pragma unroll
-      for (int j = 0; j < MP; ++j) acc[j] += (double)part[j];
+      for (int j = 0; j < MP; ++j) acc[r][j] += (double)part[j];
     }
   }
-  if (row < n) {
 #pragma unroll
-    for (int j = 0; j < MP; ++j)
-      if (j < m) {
-        double v = acc[j];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) Cout[row * m + j] = (T)v;
-      }
-  }
+  for (int r = 0; r < kSkinnyRows; ++r)
+    if (row0 + r < n) {
+#pragma unroll
+      for (int j = 0; j < MP; ++j)
+        if (j < m) {
+          double v = acc[r][j];
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) Cout[(row0 + r) * m + j] = (T)v;
+        }
+    }
 }
 
 // dA[n][k] = sum_j G[n][j] * B[k][j]: threads over k (coalesced writes), B row in registers
@@ -481,9 +489,10 @@ __global__ void __launch_bounds__(256) skinny_db_finish(const double* __restrict
 template <typename T, int MP>
 int skinny_mp(int which, long long n, int d, int m, const T* a, const T* b, T* out, cudaStream_t st) {
   if (which == 0) {
-    int ch = std::max(32, std::min(1024, (int)(40960 / (MP * sizeof(T))) / 32 * 32));   // <= 40 KB of smem
-    size_t smem = (size_t)ch * MP * sizeof(T);
-    skinny_fwd_kernel<T, MP><<<(unsigned)((n + 7) / 8), 256, smem, st>>>(a, b, out, n, d, m, ch);
+    int ch = std::max(32, std::min(1024, (int)(40960 / (MP * sizeof(T))) / 32 * 32 - 32));   // <= 40 KB of smem
+    size_t smem = (size_t)(ch + 1) * MP * sizeof(T);
+    const long long rows_per_block = 8 * kSkinnyRows;
+    skinny_fwd_kernel<T, MP><<<(unsigned)((n + rows_per_block - 1) / rows_per_block), 256, smem, st>>>(a, b, out, n, d, m, ch);
     MGB_LAUNCH_CHECK();
   } else if (which == 1) {
     dim3 grid((d + 255) / 256, (unsigned)((n + 63) / 64));

@@ -73,6 +73,8 @@ def dtype_code(dtype) -> int:
 # while it was alive, or ``record_stream`` named a side stream — is not cached: it goes back
 # to the driver pool behind events that order the free after the work on those streams.
 _CACHE: dict = {}          # (device, stream, nbytes) -> [ptr, ...]
+_GRAPH_STREAMS: set = set()   # streams owned by a live StepGraph: their cached blocks are part of the recorded graph
+_capturing: bool = False      # inside StepGraph capture: a cache miss would put a graph-owned allocation into the graph
 _CACHE_LIMIT = int(float(os.environ.get("MGB_CACHE_LIMIT", 32e9)))   # bytes kept at most
 _cached_bytes = 0
 
@@ -86,15 +88,18 @@ def empty_cache() -> None:
     """returns every cached block to the driver's stream-ordered pool"""
     global _cached_bytes
     cur = _device()
-    for (dev, stream, _), ptrs in list(_CACHE.items()):
+    for key, ptrs in list(_CACHE.items()):
+        dev, stream, nbytes = key
+        if stream in _GRAPH_STREAMS:      # a recorded graph replays into these blocks: they stay
+            continue
         if dev != cur:
             lib.mgb_set_device(dev)
         for p in ptrs:
             lib.mgb_free_async(C.c_void_p(p), C.c_void_p(stream))
         if dev != cur:
             lib.mgb_set_device(cur)
-    _CACHE.clear()
-    _cached_bytes = 0
+        _cached_bytes -= nbytes * len(ptrs)
+        del _CACHE[key]
 
 
 def _order_after(stream: int, others) -> None:
@@ -127,6 +132,10 @@ class _Allocation:
             self.ptr = free.pop()
             _cached_bytes -= self.nbytes
             return
+        if _capturing:
+            raise RuntimeError(
+                f"StepGraph: the captured step asked for a {self.nbytes}-byte block the warm-up steps never freed "
+                "(its allocations differ from step to step); graphs need a step whose buffer sizes repeat")
         p = C.c_void_p()
         rc = lib.mgb_malloc_async(C.byref(p), C.c_size_t(self.nbytes), C.c_void_p(_stream))
         if rc != 0 and _cached_bytes:

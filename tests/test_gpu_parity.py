@@ -319,6 +319,44 @@ def test_wgrad_row_halo_vs_oracle(case, rows, monkeypatch):
     assert_close(wt.grad.get(), want, np.float32, err_msg=f"rows={rows} dw {case}")
 
 
+THIN_CASES = [
+    # N, C, F, X, W, stride, padding, dilation: few input channels (C * taps <= 64) — conv_thin.cuh
+    (4, 3, 32, (32, 32), (3, 3), 1, 1, 1),               # config 5, layer 1 in small
+    (3, 3, 16, (20, 18), (3, 3), 1, 1, 1),               # config 1: 16 filters
+    (2, 3, 70, (17, 23), (3, 3), (2, 1), (1, 0), 1),      # 70 filters: two filter groups; stride 2 on the rows
+    (2, 1, 8, (30, 30), (5, 5), 1, 2, 2),                # one channel, dilation 2
+    (2, 4, 24, (9, 40), (2, 7), (1, 3), (0, 3), 1),       # 56 taps x channels; stride 3 on the columns
+    (3, 2, 40, (51,), (9,), 2, 4, 1),                    # 1-D
+    (2, 3, 12, (6, 10, 9), (2, 3, 3), 1, (0, 1, 1), 1),   # 3-D: generic gather variants
+    (2, 3, 32, (70, 70), (3, 3), 1, 1, 1),               # rows longer than one band pass; several bands per sample
+]
+
+
+@pytest.mark.parametrize("case", THIN_CASES, ids=lambda c: "x".join(map(str, c[:3])) + f"_{len(c[3])}d")
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("path", ["mma", "fma", "off"])
+def test_conv_thin_paths_vs_oracle(case, dtype, path, monkeypatch):
+    """thin layers: band-staged mma.sync 3xTF32 kernels (float32), band-staged / gather FMA kernels (both dtypes),
+    and the generic MMA tiles (MGB_CONV_THIN=0), forward + dX + dW against the oracle"""
+    monkeypatch.setenv("MGB_CONV_THIN", "0" if path == "off" else "1")
+    monkeypatch.setenv("MGB_THIN_MMA", "1" if path == "mma" else "0")
+    N, C, F, X, W, s, p, d = case
+    rng = np.random.default_rng(hash(case) % (2 ** 32))
+    x = rng.standard_normal((N, C, *X)).astype(dtype)
+    w = rng.standard_normal((F, C, *W)).astype(dtype)
+    xt, wt = Tensor(x), Tensor(w)
+    y = conv_nd(xt, wt, stride=s, padding=p, dilation=d)
+    x64, w64 = x.astype(np.float64), w.astype(np.float64)
+    want = oc.conv_fwd(x64, w64, s, p, d)
+    assert y.shape == want.shape
+    assert_close(y.numpy(), want, dtype, err_msg=f"{path} fwd {case}")
+    g = rng.standard_normal(want.shape).astype(dtype)
+    y.backward(g)
+    g64 = g.astype(np.float64)
+    assert_close(xt.grad.get(), oc.conv_dx(g64, x.shape, w64, s, p, d), dtype, err_msg=f"{path} dx {case}")
+    assert_close(wt.grad.get(), oc.conv_dw(g64, x64, w.shape, s, p, d), dtype, err_msg=f"{path} dw {case}")
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_pool_random_vs_oracle_bit_exact(dtype):
     rng = np.random.default_rng(77)
