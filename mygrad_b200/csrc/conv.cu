@@ -304,6 +304,7 @@ int run_fwdlike(const FwdParams<T>& p, cudaStream_t st) {
     int nb, kp;
     size_t smem;
     if (thin_fwdlike_applies(p, &nb, &kp, &smem)) {
+      if (nb == 4 && (long long)p.M < 2LL * sm_count() * thin::THREADS * 4) return launch_thin_fwdlike<T, 4, 1>(p, kp, smem, st);
       if (nb == 4) return launch_thin_fwdlike<T, 4, 4>(p, kp, smem, st);
       if (nb == 16) return launch_thin_fwdlike<T, 16, 2>(p, kp, smem, st);
       return launch_thin_fwdlike<T, 32, 2>(p, kp, smem, st);
