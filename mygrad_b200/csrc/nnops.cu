@@ -354,60 +354,73 @@ constexpr int kSkinnyMaxM = 32;
 // type before adding them to a float64 total: float32 inputs keep float32 FMA rate, the long sums stay exact to
 // ~1e-7 (the reference's sgemm accumulates in float32 throughout).
 
-// C[n][j] = sum_d A[n][d] * B[d][j]: a warp owns RW rows, lanes stride d, B^T staged in smem by chunks
-// ([j][chunk + 1]: the odd stride keeps both the transposing store and the lane-strided reads conflict-free)
-constexpr int kSkinnyRows = 2;            // rows per warp: the staged chunk of B is used 16 times per block
-template <typename T, int MP>
+// C[n][j] = sum_d A[n][d] * B[d][j]: a block owns RB rows; thread t walks k = t, t + 256, ...: one row of B
+// (m contiguous values) and RB coalesced elements of A per k for RB * m FMAs, then the block sums its 256
+// partial tiles (shuffles, then warp order through shared memory: deterministic).  A is read once; B comes from L2.
+template <typename T, int MP, int RB>
 __global__ void __launch_bounds__(256) skinny_fwd_kernel(const T* __restrict__ A, const T* __restrict__ B,
-                                                         T* __restrict__ Cout, long long n, int d, int m,
-                                                         int CH) {
-  extern __shared__ unsigned char smem_raw2[];
-  T* bs = reinterpret_cast<T*>(smem_raw2);          // [MP][CH + 1]
-  const int CHP = CH + 1;
+                                                         T* __restrict__ Cout, long long n, int d, int m) {
+  __shared__ double red[8][RB * MP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row0 = ((long long)blockIdx.x * 8 + warp) * kSkinnyRows;
-  double acc[kSkinnyRows][MP];
+  const long long row0 = (long long)blockIdx.x * RB;
+  double acc[RB][MP];
 #pragma unroll
-  for (int r = 0; r < kSkinnyRows; ++r)
+  for (int r = 0; r < RB; ++r)
 #pragma unroll
     for (int j = 0; j < MP; ++j) acc[r][j] = 0.0;
-  for (int d0 = 0; d0 < d; d0 += CH) {
-    const int len = min(CH, d - d0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < len * m; i += blockDim.x) {
-      const int k = i / m, j = i - k * m;
-      bs[j * CHP + k] = B[(long long)d0 * m + i];
+  if constexpr (sizeof(T) == 8) {
+    for (int k = threadIdx.x; k < d; k += 256) {
+      T b[MP];
+#pragma unroll
+      for (int j = 0; j < MP; ++j) b[j] = j < m ? __ldg(B + (long long)k * m + j) : (T)0;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const T av = row0 + r < n ? __ldg(A + (row0 + r) * d + k) : (T)0;
+#pragma unroll
+        for (int j = 0; j < MP; ++j) acc[r][j] += av * b[j];
+      }
     }
-    if (m < MP)
-      for (int i = threadIdx.x; i < (MP - m) * len; i += blockDim.x) bs[(m + i / len) * CHP + i % len] = (T)0;
-    __syncthreads();
+  } else {
+    for (int k0 = 0; k0 < d; k0 += 256 * 64) {            // runs of <= 64 products in float32, totals in float64
+      T part[RB][MP];
 #pragma unroll
-    for (int r = 0; r < kSkinnyRows; ++r) {
-      if (row0 + r >= n) continue;
-      const T* a = A + (row0 + r) * d + d0;
-      T part[MP];
+      for (int r = 0; r < RB; ++r)
 #pragma unroll
-      for (int j = 0; j < MP; ++j) part[j] = (T)0;
-      for (int k = lane; k < len; k += 32) {            // <= CH / 32 <= 32 products per run
-        const T av = a[k];
+        for (int j = 0; j < MP; ++j) part[r][j] = (T)0;
+      for (int k = k0 + threadIdx.x; k < min(d, k0 + 256 * 64); k += 256) {
+        T b[MP];
 #pragma unroll
-        for (int j = 0; j < MP; ++j) part[j] += av * bs[j * CHP + k];
+        for (int j = 0; j < MP; ++j) b[j] = j < m ? __ldg(B + (long long)k * m + j) : (T)0;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const T av = row0 + r < n ? __ldg(A + (row0 + r) * d + k) : (T)0;
+#pragma unroll
+          for (int j = 0; j < MP; ++j) part[r][j] += av * b[j];
+        }
       }
 #pragma unroll
-      for (int j = 0; j < MP; ++j) acc[r][j] += (double)part[j];
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int j = 0; j < MP; ++j) acc[r][j] += (double)part[r][j];
     }
   }
 #pragma unroll
-  for (int r = 0; r < kSkinnyRows; ++r)
-    if (row0 + r < n) {
+  for (int r = 0; r < RB; ++r)
 #pragma unroll
-      for (int j = 0; j < MP; ++j)
-        if (j < m) {
-          double v = acc[r][j];
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0) Cout[(row0 + r) * m + j] = (T)v;
-        }
+    for (int j = 0; j < MP; ++j) {
+      double v = acc[r][j];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][r * MP + j] = v;
     }
+  __syncthreads();
+  for (int i = threadIdx.x; i < RB * MP; i += 256) {
+    const int r = i / MP, j = i - r * MP;
+    if (row0 + r < n && j < m) {
+      double v = 0.0;
+      for (int w = 0; w < 8; ++w) v += red[w][i];
+      Cout[(row0 + r) * m + j] = (T)v;
+    }
+  }
 }
 
 // dA[n][k] = sum_j G[n][j] * B[k][j]: threads over k (coalesced writes), B row in registers
@@ -489,10 +502,8 @@ __global__ void __launch_bounds__(256) skinny_db_finish(const double* __restrict
 template <typename T, int MP>
 int skinny_mp(int which, long long n, int d, int m, const T* a, const T* b, T* out, cudaStream_t st) {
   if (which == 0) {
-    int ch = std::max(32, std::min(1024, (int)(40960 / (MP * sizeof(T))) / 32 * 32 - 32));   // <= 40 KB of smem
-    size_t smem = (size_t)(ch + 1) * MP * sizeof(T);
-    const long long rows_per_block = 8 * kSkinnyRows;
-    skinny_fwd_kernel<T, MP><<<(unsigned)((n + rows_per_block - 1) / rows_per_block), 256, smem, st>>>(a, b, out, n, d, m, ch);
+    constexpr int RB = MP <= 8 ? 8 : MP <= 16 ? 4 : 2;
+    skinny_fwd_kernel<T, MP, RB><<<(unsigned)((n + RB - 1) / RB), 256, 0, st>>>(a, b, out, n, d, m);
     MGB_LAUNCH_CHECK();
   } else if (which == 1) {
     dim3 grid((d + 255) / 256, (unsigned)((n + 63) / 64));
