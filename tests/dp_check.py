@@ -40,11 +40,14 @@ def world_gt1(dp) -> bool:
     return dp.world_size > 1
 
 
-def conv_case(dp, dtype, n_total, fused: bool):
+def conv_case(dp, dtype, n_total, fused: bool, channels=(16, 32)):
+    """channels = (C, F): (16, 32) runs the generic MMA tiles, (3, 32) the thin-layer kernels (conv_thin.cuh),
+    (64, 128) the tensor-core kernels (row-halo wgrad / TMA-fed float64) — each with its own split-K partials that
+    the fused peer-memory kernel has to sum across ranks"""
     rank, world = dp.rank, dp.world_size
     rng = np.random.default_rng(11)
-    x = rng.standard_normal((n_total, 16, 10, 10)).astype(dtype)
-    w = rng.standard_normal((32, 16, 3, 3)).astype(dtype)
+    x = rng.standard_normal((n_total, channels[0], 10, 10)).astype(dtype)
+    w = rng.standard_normal((channels[1], channels[0], 3, 3)).astype(dtype)
     lo, hi = dp.shard(n_total)
     xt, wt = Tensor(x[lo:hi]), Tensor(w)
     y = conv_nd(xt, wt, stride=1, padding=1)
@@ -60,7 +63,7 @@ def conv_case(dp, dtype, n_total, fused: bool):
         dp.allreduce([wt.grad])
     want_out, want_dx, want_dw = oc.layer_step(x.astype(np.float64), w.astype(np.float64), stride=1, padding=1,
                                                dilation=1, pool=(2, 2), pool_stride=2)
-    tag = f"{np.dtype(dtype).name} N={n_total} fused={fused} rank={rank}"
+    tag = f"{np.dtype(dtype).name} N={n_total} C,F={channels} fused={fused} rank={rank}"
     if hi > lo:
         assert_close(out.numpy(), want_out[lo:hi], dtype, err_msg=f"out {tag}")
         assert_close(xt.grad.get(), want_dx[lo:hi], dtype, err_msg=f"dx {tag}")
@@ -107,6 +110,9 @@ def main():
         for n_total in (8, 3, 1):                  # even shards, uneven shards, an EMPTY shard on the last ranks
             for fused in ((True, False) if dp.peer_slot_bytes else (False,)):
                 conv_case(dp, dtype, n_total, fused)
+        for channels in ((3, 32), (64, 128)):
+            for fused in ((True, False) if dp.peer_slot_bytes else (False,)):
+                conv_case(dp, dtype, 5, fused, channels)
         batchnorm_case(dp, dtype)
     # many back-to-back collectives: slot parity / epoch protocol
     buf = mg.asdevice(np.full(1000, float(rank + 1), np.float32))
