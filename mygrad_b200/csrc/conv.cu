@@ -1246,7 +1246,10 @@ int wgrad_rows_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const f
     if (L.cblocks % c == 0 && p.W[1] * c <= 8) { cbc = c; break; }
   if (cbc == 0 || (cbc > 1 && p.D[1] != 1)) return 2;
   const int ncols = p.W[1] * cbc * 32;
-  if (ncols < 128 && !(er && er[0] == '1')) return 2;
+  // F <= 64: fold two column taps into the two halves of the 128 UMMA lanes (conv_wgrad2.cuh); MGB_WGRAD_FOLD=0 disables
+  const char* efold = getenv("MGB_WGRAD_FOLD");
+  const bool fold = p.F <= 64 && p.S[2] == 1 && p.W[2] >= 2 && !(efold && efold[0] == '0');
+  if (ncols < (fold ? 96 : 128) && !(er && er[0] == '1')) return 2;
   const int ext = (p.W[1] - 1) * p.D[1];
   // pixel box b1 x b2 = 32 with b2 >= 4: fewest x bytes per stage over all boxes
   int b1 = 0, b2 = 0;
@@ -1261,7 +1264,8 @@ int wgrad_rows_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const f
   if (best < 0) return 2;
   tma::WgradRowsParams wp;
   wp.b1 = b1; wp.b2 = b2;
-  wp.tiles1 = (p.G[1] + b1 - 1) / b1; wp.tiles2 = (p.G[2] + b2 - 1) / b2;
+  wp.fold = fold ? 1 : 0;
+  wp.tiles1 = (p.G[1] + b1 - 1) / b1; wp.tiles2 = (p.G[2] + (fold ? p.D[2] : 0) + b2 - 1) / b2;
   wp.G0 = p.G[0]; wp.X0 = p.X[0];
   wp.S0 = p.S[0]; wp.S2 = p.S[2]; wp.Pd1 = p.Pd[1]; wp.Pd2 = p.Pd[2];
   wp.D0 = p.D[0]; wp.D1 = p.D[1]; wp.D2 = p.D[2];
@@ -1271,7 +1275,7 @@ int wgrad_rows_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const f
   wp.tmem_cols = pow2_cols(ncols);
   const long long boxes = (long long)p.N * p.G[0] * wp.tiles1 * wp.tiles2;
   if (boxes > INT32_MAX || (long long)p.N * std::max(p.G[0], p.X[0]) > INT32_MAX) return 2;
-  const int ny = p.W[0] * p.W[2] * (L.cblocks / cbc);
+  const int ny = p.W[0] * (fold ? (p.W[2] + 1) / 2 : p.W[2]) * (L.cblocks / cbc);
   int splits = (int)std::max<long long>(1, std::min<long long>(std::max(1, sm_count() / (L.mt * ny)), boxes / 8));
   const long long per = (boxes + splits - 1) / splits;
   splits = (int)((boxes + per - 1) / per);
@@ -1285,7 +1289,7 @@ int wgrad_rows_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const f
     const cuuint64_t row = (cuuint64_t)L.Y.cpad * 4;
     cuuint64_t dims[5] = {32, (cuuint64_t)p.G[2], (cuuint64_t)p.G[1], (cuuint64_t)p.N * p.G[0], (cuuint64_t)L.Y.cpad / 32};
     cuuint64_t strides[4] = {row, row * p.G[2], row * p.G[2] * p.G[1], 128};
-    cuuint32_t box[5] = {32, (cuuint32_t)b2, (cuuint32_t)b1, 1, 4};
+    cuuint32_t box[5] = {32, (cuuint32_t)b2, (cuuint32_t)b1, 1, (cuuint32_t)(fold ? 2 : 4)};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,

@@ -18,6 +18,12 @@
 //
 // Needs: conv stride 1 along the middle axis, dilation 1 along it when a CTA holds several c-blocks, boxes that
 // do not span samples, W1 * cbc <= 8.  Everything else goes to wgrad_tma_kernel.
+//
+// FOLD (F <= 64): a 128-lane UMMA with 64 filters wastes half of every instruction.  The upper 64 lanes then get
+// the SAME filters' dy shifted by delta = D2 pixels along the innermost axis:
+//     D[64 + f, (tap, c)] = sum_pixels dy[pixel + delta, f] * x[pixel + tap, c] = dw[f, c, tap - 1 column tap]
+// so one CTA covers the column taps dc and dc - 1 and two CTAs cover three.  The pixel boxes start delta columns
+// early (those columns of the unshifted dy are TMA zero fill), conv stride 1 along that axis.
 #pragma once
 #include "conv_tma.cuh"
 
@@ -36,6 +42,7 @@ struct WgradRowsParams {
   int rows;                                // halo rows: b1 + (W1 - 1) * D1
   int boxes_total, boxes_per_split;
   int tmem_cols;
+  int fold;                                // 1: lanes 64..127 hold dy shifted by D2 columns (F <= 64), see above
   unsigned long long* prof;                // MGB_WGRAD_PROF: [cta][4] = wait-full clocks, loop clocks, stages
 };
 
@@ -65,8 +72,12 @@ wgrad_rows_kernel(const __grid_constant__ WgradRowsParams p, const __grid_consta
   int y = blockIdx.y;
   const int ncbg = p.cblocks / p.cbc;
   const int cb0 = (y % ncbg) * p.cbc; y /= ncbg;
-  const int dc = y % p.W2;
-  const int t0 = y / p.W2;
+  const int ndc = p.fold ? (p.W2 + 1) / 2 : p.W2;        // column-tap CTAs
+  const int jdc = y % ndc;
+  const int dc = p.fold ? min(2 * jdc + 1, p.W2 - 1) : jdc;
+  const bool upper = p.fold && dc >= 1 && (2 * jdc + 1 <= p.W2 - 1);   // lanes 64..127 own column tap dc - 1
+  const int shift = p.fold ? p.D2 : 0;                    // boxes start this many columns early
+  const int t0 = y / ndc;
   const int nblk = p.W1 * p.cbc;                         // operand blocks of the N tile: (dr, cb)
   const int kb0 = blockIdx.z * p.boxes_per_split;
   const int kb1 = min(p.boxes_total, kb0 + p.boxes_per_split);
@@ -100,15 +111,22 @@ wgrad_rows_kernel(const __grid_constant__ WgradRowsParams p, const __grid_consta
         const int t1 = kb % p.tiles1; kb /= p.tiles1;
         const int u = kb;                                 // n * G0 + g0
         const int n = u / p.G0, g0 = u - n * p.G0;
-        const int g1 = t1 * p.b1, g2 = t2 * p.b2;
+        const int g1 = t1 * p.b1, g2 = t2 * p.b2 - shift;
         const int ux = n * p.X0 + g0 * p.S0 + t0 * p.D0;  // the outermost axis is unpadded
         const int x1 = g1 - p.Pd1;
         const int x2 = g2 * p.S2 - p.Pd2 + dc * p.D2;
         const uint32_t a_hi = smem_base + stage * stage_bytes;
         const uint32_t b_hi = a_hi + 2 * a_plane;
         mbar_expect_tx(full_bar + stage, tx);
-        tma_load_5d(a_hi, &map_dy_hi, full_bar + stage, 0, g2, g1, u, m0 / 32);
-        tma_load_5d(a_hi + a_plane, &map_dy_lo, full_bar + stage, 0, g2, g1, u, m0 / 32);
+        if (p.fold) {       // two filter blocks unshifted, the same two shifted by D2 columns
+          tma_load_5d(a_hi, &map_dy_hi, full_bar + stage, 0, g2, g1, u, 0);
+          tma_load_5d(a_hi + a_plane / 2, &map_dy_hi, full_bar + stage, 0, g2 + shift, g1, u, 0);
+          tma_load_5d(a_hi + a_plane, &map_dy_lo, full_bar + stage, 0, g2, g1, u, 0);
+          tma_load_5d(a_hi + a_plane + a_plane / 2, &map_dy_lo, full_bar + stage, 0, g2 + shift, g1, u, 0);
+        } else {
+          tma_load_5d(a_hi, &map_dy_hi, full_bar + stage, 0, g2, g1, u, m0 / 32);
+          tma_load_5d(a_hi + a_plane, &map_dy_lo, full_bar + stage, 0, g2, g1, u, m0 / 32);
+        }
         tma_load_5d(b_hi, &map_x_hi, full_bar + stage, 0, x2, cb0, x1, ux);
         tma_load_5d(b_hi + b_plane, &map_x_lo, full_bar + stage, 0, x2, cb0, x1, ux);
       }
@@ -157,7 +175,10 @@ wgrad_rows_kernel(const __grid_constant__ WgradRowsParams p, const __grid_consta
   } else {
     // ===== epilogue: lane = f, columns = (dr, cb, channel) -> partial[f][c][tap] =====
     const int quarter = warp & 3;
-    const int f = m0 + quarter * 32 + lane;
+    int f = m0 + quarter * 32 + lane;
+    int dcw = dc;                                          // column tap this lane writes
+    bool wr = true;
+    if (p.fold && f >= 64) { f -= 64; dcw = dc - 1; wr = upper; }
     float* out = p.partial + (long long)blockIdx.z * p.F * p.C * p.Wp;
     if (S > 0) {
       tc::mbar_wait(accum_bar, 0);
@@ -174,8 +195,8 @@ wgrad_rows_kernel(const __grid_constant__ WgradRowsParams p, const __grid_consta
       }
       const int b = col >> 5;
       const int dr = b / p.cbc, cb = cb0 + (b - dr * p.cbc);
-      const int tap = (t0 * p.W1 + dr) * p.W2 + dc;
-      if (f < p.F) {
+      const int tap = (t0 * p.W1 + dr) * p.W2 + dcw;
+      if (wr && f < p.F) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int c = cb * 32 + (col & 31) + j;

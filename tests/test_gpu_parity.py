@@ -299,6 +299,11 @@ WGRAD_ROWS_CASES = [
     (2, 32, 64, (6, 10, 10), (3, 3, 3), 1, 0, 1),
     (2, 64, 128, (6, 9, 12), (2, 3, 3), (2, 1, 1), (0, 1, 1), 1),
     (2, 64, 128, (40,), (5,), 1, 2, 1),
+    # F <= 64: two column taps folded into the two halves of the 128 UMMA lanes (dy shifted by D2 columns)
+    (3, 32, 64, (14, 15), (3, 2), 1, (1, 0), 1),        # two column taps: one CTA covers both
+    (2, 32, 48, (12, 13), (3, 5), 1, (1, 2), 1),        # five column taps, 48 filters
+    (2, 64, 64, (9, 21), (3, 3), 1, 1, (1, 3)),         # dilation 3 along the folded axis: shift by 3 columns
+    (2, 32, 33, (5, 9, 11), (2, 3, 3), 1, (0, 1, 1), 1),  # 3-D, 33 filters
 ]
 
 
