@@ -1,3 +1,4 @@
+# 8-GPU re-run of the two workloads the folded wgrad changed (run under gpurun --gpus 8): config 4 strong scaling, config 5 weak
 N=8
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
 run 29623 bench.py --gpus $N --steps 10 --warmup 3 --workload C4 --scaling strong --no-e2e > gpurun_out/scale_C4_strong_n$N.json 2> gpurun_out/scale_C4_strong_n$N.err; echo "C4 strong rc=$?"
