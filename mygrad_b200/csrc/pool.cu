@@ -143,6 +143,53 @@ __global__ void __launch_bounds__(256) pool_max_fwd_vec(PoolGeom g, const T* __r
   }
 }
 
+// Rows that are only 2-vector aligned (X2 = 62 floats in config 4: 248-byte rows) cannot use the 16-byte
+// kernel above, and the one-window pair kernel keeps just P0*P1 eight-byte loads in flight per thread (0.53 of
+// HBM).  Here a thread owns VW consecutive windows of one output row and issues all VW * P0 * P1 two-element
+// loads before the first compare; the last group of a row is ragged (predicated).
+template <typename T, int VW, int MAXROWS>
+__global__ void __launch_bounds__(256) pool_max_fwd_pairs(PoolGeom g, const T* __restrict__ x,
+                                                          T* __restrict__ y, long long total_groups) {
+  using V = typename Vec2<T>::type;
+  const int gv = (g.G[2] + VW - 1) / VW;
+  const int rows = g.P[0] * g.P[1];            // <= MAXROWS (checked on the host)
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total_groups;
+       o += (long long)gridDim.x * blockDim.x) {
+    long long t = o;
+    const int v2 = (int)(t % gv); t /= gv;
+    const int g1 = (int)(t % g.G[1]); t /= g.G[1];
+    const int g0 = (int)(t % g.G[0]);
+    const long long l = t / g.G[0];
+    // the thread's windows are v2, v2 + gv, v2 + 2 gv, ...: neighbouring threads touch neighbouring windows
+    // in every load / store instruction (whole 32-byte sectors), not VW windows apart
+    const T* base = x + l * g.x_per_lead +
+                    ((long long)(g0 * g.S[0]) * g.X[1] + g1 * g.S[1]) * g.X[2];
+    V raw[MAXROWS][VW];
+#pragma unroll
+    for (int r = 0; r < MAXROWS; ++r)
+      if (r < rows) {
+        const int p0 = r / g.P[1], p1 = r - p0 * g.P[1];
+        const V* row = reinterpret_cast<const V*>(base + ((long long)p0 * g.X[1] + p1) * g.X[2]);
+#pragma unroll
+        for (int w = 0; w < VW; ++w)
+          if (v2 + w * gv < g.G[2]) raw[r][w] = __ldg(row + v2 + w * gv);
+      }
+    T* dst = y + l * g.g_per_lead + ((long long)g0 * g.G[1] + g1) * g.G[2];
+#pragma unroll
+    for (int w = 0; w < VW; ++w)
+      if (v2 + w * gv < g.G[2]) {
+        T best = raw[0][w].x;
+#pragma unroll
+        for (int r = 0; r < MAXROWS; ++r)
+          if (r < rows) {
+            if (r > 0 && beats(raw[r][w].x, best)) best = raw[r][w].x;
+            if (beats(raw[r][w].y, best)) best = raw[r][w].y;
+          }
+        dst[v2 + w * gv] = best;
+      }
+  }
+}
+
 // ---- backward --------------------------------------------------------------
 
 // window-centric, for exact non-overlapping tilings (S == P on every axis) whose
@@ -183,6 +230,67 @@ __global__ void __launch_bounds__(256) pool_max_bwd_tile_pair(PoolGeom g, const 
         out.y = (arg == idx + 1) ? gval : (T)0;
         *reinterpret_cast<V*>(dx + off + ((long long)p0 * g.X[1] + p1) * g.X[2]) = out;
         idx += 2;
+      }
+  }
+}
+
+// window-centric, exact tiling, rows only 2-vector aligned: VW windows per thread, all loads first (see
+// pool_max_fwd_pairs); the first maximum in row-major window order takes dy, the rest of the window zeros
+template <typename T, int VW, int MAXROWS>
+__global__ void __launch_bounds__(256) pool_max_bwd_tile_pairs(PoolGeom g, const T* __restrict__ dy,
+                                                               const T* __restrict__ x, T* __restrict__ dx,
+                                                               long long total_groups) {
+  using V = typename Vec2<T>::type;
+  const int gv = (g.G[2] + VW - 1) / VW;
+  const int rows = g.P[0] * g.P[1];
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total_groups;
+       o += (long long)gridDim.x * blockDim.x) {
+    long long t = o;
+    const int v2 = (int)(t % gv); t /= gv;
+    const int g1 = (int)(t % g.G[1]); t /= g.G[1];
+    const int g0 = (int)(t % g.G[0]);
+    const long long l = t / g.G[0];
+    const long long off = l * g.x_per_lead +
+                          ((long long)(g0 * g.P[0]) * g.X[1] + g1 * g.P[1]) * g.X[2];
+    V raw[MAXROWS][VW];
+#pragma unroll
+    for (int r = 0; r < MAXROWS; ++r)
+      if (r < rows) {
+        const int p0 = r / g.P[1], p1 = r - p0 * g.P[1];
+        const V* row = reinterpret_cast<const V*>(x + off + ((long long)p0 * g.X[1] + p1) * g.X[2]);
+#pragma unroll
+        for (int w = 0; w < VW; ++w)
+          if (v2 + w * gv < g.G[2]) raw[r][w] = __ldg(row + v2 + w * gv);
+      }
+    const T* gsrc = dy + l * g.g_per_lead + ((long long)g0 * g.G[1] + g1) * g.G[2];
+    T gval[VW];
+    int arg[VW];
+#pragma unroll
+    for (int w = 0; w < VW; ++w)
+      if (v2 + w * gv < g.G[2]) {
+        gval[w] = __ldg(gsrc + v2 + w * gv);
+        T best = raw[0][w].x;
+        arg[w] = 0;
+#pragma unroll
+        for (int r = 0; r < MAXROWS; ++r)
+          if (r < rows) {
+            if (r > 0 && beats(raw[r][w].x, best)) { best = raw[r][w].x; arg[w] = 2 * r; }
+            if (beats(raw[r][w].y, best)) { best = raw[r][w].y; arg[w] = 2 * r + 1; }
+          }
+      }
+#pragma unroll
+    for (int r = 0; r < MAXROWS; ++r)
+      if (r < rows) {
+        const int p0 = r / g.P[1], p1 = r - p0 * g.P[1];
+        V* row = reinterpret_cast<V*>(dx + off + ((long long)p0 * g.X[1] + p1) * g.X[2]);
+#pragma unroll
+        for (int w = 0; w < VW; ++w)
+          if (v2 + w * gv < g.G[2]) {
+            V out;
+            out.x = (arg[w] == 2 * r) ? gval[w] : (T)0;
+            out.y = (arg[w] == 2 * r + 1) ? gval[w] : (T)0;
+            row[v2 + w * gv] = out;
+          }
       }
   }
 }
@@ -346,6 +454,9 @@ int pool_fwd_t(const PoolGeom& g, int mode, const T* x, T* y, cudaStream_t st) {
   if (vec) {
     long long tv = total / VW;
     pool_max_fwd_vec<T, VW><<<grid_for(tv, 256), 256, 0, st>>>(g, x, y, tv);
+  } else if (pair && g.P[0] * g.P[1] <= 4) {
+    const long long groups = g.lead * g.G[0] * g.G[1] * ((g.G[2] + 3) / 4);
+    pool_max_fwd_pairs<T, 4, 4><<<grid_for(groups, 256), 256, 0, st>>>(g, x, y, groups);
   } else if (pair)
     pool_max_fwd_pair<T><<<grid, 256, 0, st>>>(g, x, y, total);
   else if (mode == 0)
@@ -370,6 +481,9 @@ int pool_bwd_t(const PoolGeom& g, int mode, const T* dy, const T* x, T* dx, cuda
   if (vec) {
     long long tv = total_g / VW;
     pool_max_bwd_tile_vec<T, VW, 4><<<grid_for(tv, 256), 256, 0, st>>>(g, dy, x, dx, tv);
+  } else if (pair && g.P[0] * g.P[1] <= 4) {
+    const long long groups = g.lead * g.G[0] * g.G[1] * ((g.G[2] + 3) / 4);
+    pool_max_bwd_tile_pairs<T, 4, 4><<<grid_for(groups, 256), 256, 0, st>>>(g, dy, x, dx, groups);
   } else if (pair) {
     pool_max_bwd_tile_pair<T><<<grid_for(total_g, 256), 256, 0, st>>>(g, dy, x, dx, total_g);
   } else if (mode == 0) {
