@@ -274,7 +274,7 @@ int thin2d_fwd(const Plan& p, const T* x, const T* w, T* y, cudaStream_t st) {
       const int fb = (int)std::min<long long>(p.F, 64);
       const int nt = fb <= 8 ? 1 : fb <= 16 ? 2 : fb <= 32 ? 4 : 8;
       const int kp8 = (K + 7) / 8 * 8, np = nt * 8 + ((nt * 8) % 32 == 0 ? 8 : 0);
-      const size_t sm = (size_t)2 * kp8 * np * 4 + (size_t)kp8 * 4 + t.band_bytes;
+      const size_t sm = (size_t)2 * kp8 * np * 4 + (size_t)kp8 * 4 + (((size_t)t.R * p.G[2] + 3) & ~(size_t)3) * 4 + t.band_bytes;
       if (sm <= 48 * 1024) {
         const int gy2 = (int)((p.F + nt * 8 - 1) / (nt * 8));
         const int gx2 = (int)std::min<long long>(p.N * t.nbands, std::max(1, 4 * sm_count() / gy2));

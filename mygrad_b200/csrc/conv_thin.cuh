@@ -184,16 +184,22 @@ struct Thin2dParams {
 
 template <typename T>
 __device__ __forceinline__ void thin2d_load_band(const Thin2dParams<T>& p, T* band, int n, int r0, int tid, int nthreads) {
-  const int per_c = p.RB * p.CBp;
-  const int total = p.C * per_c;
+  // a warp takes whole (channel, band row) rows, its lanes walk the columns: one division per row, none per element
+  const int nrows = p.C * p.RB;
   const T* xs = p.x + (long long)n * p.C * p.X1 * p.X2;
   const int x1_0 = r0 * p.s1 - p.p1, x2_0 = -p.p2;
-  for (int i = tid; i < total; i += nthreads) {
-    const int c = i / per_c, rem = i - c * per_c;
-    const int rb = rem / p.CBp, cb = rem - rb * p.CBp;
-    const int x1 = x1_0 + rb, x2 = x2_0 + cb;
-    const bool v = cb < p.CB && (unsigned)x1 < (unsigned)p.X1 && (unsigned)x2 < (unsigned)p.X2;
-    cp_async_zfill<sizeof(T)>(band + i, v ? xs + ((long long)c * p.X1 + x1) * p.X2 + x2 : xs, v);
+  const int lane = tid & 31, nwarps = nthreads >> 5;
+  for (int row = tid >> 5; row < nrows; row += nwarps) {
+    const int c = row / p.RB, rb = row - c * p.RB;
+    const int x1 = x1_0 + rb;
+    const bool rv = (unsigned)x1 < (unsigned)p.X1;
+    const T* src = xs + ((long long)c * p.X1 + (rv ? x1 : 0)) * p.X2;
+    T* dst = band + row * p.CBp;
+    for (int cb = lane; cb < p.CBp; cb += 32) {
+      const int x2 = x2_0 + cb;
+      const bool v = rv && cb < p.CB && (unsigned)x2 < (unsigned)p.X2;
+      cp_async_zfill<sizeof(T)>(dst + cb, v ? src + x2 : xs, v);
+    }
   }
 }
 
@@ -375,8 +381,13 @@ __global__ void __launch_bounds__(256) thin2d_fwd_mma_kernel(const __grid_consta
   uint32_t* whi = reinterpret_cast<uint32_t*>(thin_smem);
   uint32_t* wlo = whi + KP8 * NP;
   int* koff = reinterpret_cast<int*>(wlo + KP8 * NP);
-  float* band = reinterpret_cast<float*>(koff + KP8);
+  int* pixoff = koff + KP8;                              // band offset of pixel q of a band: [R * G2], built once
+  float* band = reinterpret_cast<float*>(pixoff + ((p.R * p.G2 + 3) & ~3));
   const int f0 = blockIdx.y * (NT * 8);
+  for (int q = threadIdx.x; q < p.R * p.G2; q += 256) {
+    const int r = q / p.G2, c = q - r * p.G2;
+    pixoff[q] = r * p.s1 * p.CBp + c * p.s2;
+  }
   for (int i = threadIdx.x; i < KP8 * NP; i += 256) {
     const int k = i / NP, n = i - k * NP;
     const float v = (k < K && n < NT * 8 && f0 + n < p.F) ? p.w[(long long)(f0 + n) * K + k] : 0.f;
@@ -411,8 +422,7 @@ __global__ void __launch_bounds__(256) thin2d_fwd_mma_kernel(const __grid_consta
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int q = q0 + mt * 16 + g + h * 8;
-          const int r = q / p.G2, c = q - r * p.G2;
-          xo[mt][h] = q < npix ? r * p.s1 * p.CBp + c * p.s2 : 0;
+          xo[mt][h] = q < npix ? pixoff[q] : 0;
         }
       float acc[MT][NT][4];
 #pragma unroll
