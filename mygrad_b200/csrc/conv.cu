@@ -1105,7 +1105,9 @@ int wgrad_tma_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const fl
   // blocked maps need the channel-block axis as a fifth dimension, so batch and axis 0 share one
   // (trivially with <= 2 spatial dims; otherwise axis 0 must be unpadded and tiled exactly by the
   // boxes), and the CTA's (tap, c-block) ranges must be whole taps
-  const bool flat = p.X[0] == 1 && p.G[0] == 1;              // <= 2 spatial dims
+  // <= 2 spatial dims.  (X0 = G0 = 1 alone is not enough: a 3-tap outer axis with padding 1 also has them, and its
+  // taps would walk into the neighbouring SAMPLE of the merged (batch, axis 0) dimension — found by scripts/fuzz_conv.py)
+  const bool flat = p.X[0] == 1 && p.G[0] == 1 && p.W[0] == 1 && p.Pd[0] == 0;
   const bool mergeable = !flat && p.Pd[0] == 0;               // 3-D with an unpadded outer axis
   wp.blocked = ((flat || mergeable) && L.nbpc % L.cblocks == 0) ? 1 : 0;
   // pixels per pipeline stage: 32 (2 stages) by default; MGB_WGRAD_PIX=16 -> 16-pixel stages, 5 of them
@@ -1237,7 +1239,9 @@ int wgrad_rows_launch(const Plan& p, TcWgradLayout& L, const float* xhi, const f
   const char* er = getenv("MGB_WGRAD_ROWS");
   if (!enc || !tma_enabled() || (er && er[0] == '0')) return 2;
   for (int i = 0; i < 3; ++i) if (p.X[i] < 1 || p.G[i] < 1) return 2;
-  const bool flat = p.X[0] == 1 && p.G[0] == 1;              // <= 2 spatial dims
+  // <= 2 spatial dims.  (X0 = G0 = 1 alone is not enough: a 3-tap outer axis with padding 1 also has them, and its
+  // taps would walk into the neighbouring SAMPLE of the merged (batch, axis 0) dimension — found by scripts/fuzz_conv.py)
+  const bool flat = p.X[0] == 1 && p.G[0] == 1 && p.W[0] == 1 && p.Pd[0] == 0;
   const bool mergeable = !flat && p.Pd[0] == 0;               // 3-D with an unpadded outer axis
   if (!(flat || mergeable) || p.S[1] != 1) return 2;
   // c-blocks per CTA: the N tile is W1 * cbc blocks of 32 columns, at most 8

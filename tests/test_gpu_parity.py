@@ -221,6 +221,10 @@ TC_CASES = [
     (3, 32, 32, (40,), (7,), 1, 3, 1),
     (17, 32, 160, (4, 5), (3, 3), 1, 1, 1),
     (2, 32, 32, (9, 20, 12), (3, 3, 3), 1, (1, 0, 1), 1),
+    # an outer axis of extent 1 with three taps and padding 1 (found by scripts/fuzz_conv.py): X0 = G0 = 1 like a 2-D
+    # layer, but the taps of a merged (batch, axis 0) TMA dimension would walk into the neighbouring sample
+    (2, 24, 48, (1, 5, 9), (3, 2, 1), 1, (1, 2, 1), (1, 2, 1)),
+    (3, 64, 128, (1, 12, 12), (3, 3, 3), 1, 1, 1),
 ]
 
 
