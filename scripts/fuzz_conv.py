@@ -1,6 +1,6 @@
 """Random conv_nd shapes against the NumPy oracle: forward, dX and dW, float32 and float64, 1-3 spatial dims,
 random stride / padding / dilation, channel counts on both sides of every kernel-family threshold (thin layers,
-mma.sync tiles, tcgen05 halo / row-halo / folded kernels, TMA-fed DMMA).  usage: python scripts/fuzz_conv.py [cases] [seed]"""
+mma.sync tiles, tcgen05 halo / row-halo / folded kernels, TMA-fed DMMA).  usage: python scripts/fuzz_conv.py [cases] [seed] [big]"""
 import sys
 import time
 from pathlib import Path
@@ -15,6 +15,7 @@ from oracle import conv_pool_oracle as oc
 
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+big = len(sys.argv) > 3 and sys.argv[3] == "big"       # larger extents: more tiles, more K splits, ragged boxes
 rng = np.random.default_rng(seed)
 CH = [1, 2, 3, 5, 8, 16, 24, 32, 48, 64, 96]
 FS = [1, 4, 16, 32, 33, 48, 64, 96, 100, 128, 160]
@@ -31,10 +32,10 @@ for it in range(cases):
     d = tuple(int(rng.choice([1, 1, 1, 2])) for _ in range(nd))
     p = tuple(int(rng.integers(0, 3)) for _ in range(nd))
     # output extent first, input extent from it: always a valid geometry
-    hi = {1: 200, 2: 40, 3: 12}[nd]
+    hi = {1: 600, 2: 90, 3: 22}[nd] if big else {1: 200, 2: 40, 3: 12}[nd]
     G = tuple(int(rng.integers(1, hi)) for _ in range(nd))
     X = tuple((g - 1) * si + (w - 1) * di + 1 - 2 * pi for g, si, w, di, pi in zip(G, s, W, d, p))
-    if any(x < 1 for x in X) or N * C * int(np.prod(X)) > 4e6 or N * F * int(np.prod(G)) > 4e6:
+    if any(x < 1 for x in X) or N * C * int(np.prod(X)) > (2e7 if big else 4e6) or N * F * int(np.prod(G)) > (2e7 if big else 4e6):
         continue
     ran += 1
     x = rng.standard_normal((N, C, *X)).astype(dtype)
