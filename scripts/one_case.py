@@ -9,7 +9,7 @@ from mygrad_b200 import Tensor
 from mygrad_b200.nnet.layers import conv_nd
 from oracle import conv_pool_oracle as oc
 
-xs, ws, s, p, d, dtype = (2, 24, 1, 5, 9), (48, 24, 3, 2, 1), (1, 1, 1), (1, 2, 1), (1, 2, 1), np.float32
+xs, ws, s, p, d, dtype = (4, 96, 2, 13, 19), (160, 96, 3, 3, 3), (1, 1, 1), (2, 0, 1), (1, 2, 2), np.float32
 rng = np.random.default_rng(0)
 x = rng.standard_normal(xs).astype(dtype); w = rng.standard_normal(ws).astype(dtype)
 x64, w64 = x.astype(np.float64), w.astype(np.float64)
